@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* from the REFERENCE ITSELF (oracle/_ref = unmodified
+serial_new/sweep-tt-multistart.c compiled in the build container).
+
+  python tools/make_golden.py small     -> tests/golden/small_cases.npz   (seconds)
+  python tools/make_golden.py full      -> tests/golden/full_241.json     (~15-25 min, 5 processes)
+
+The GPU box has no /root/reference; the parity tests there compare against these files.
+Small cases: converged float32 fields for seeded boxes.  Full size (BASELINE configs 1 and 2):
+sha256 of the converged field + every 4999th float + the reference's sweep count.
+"""
+import hashlib
+import json
+import multiprocessing as mp
+import pathlib
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import oracle  # noqa: E402
+from uoparallel_seismic_project_b200 import workloads as W  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+SMALL = [
+    # name, dims, field kind, seed, star, starts
+    ("rand_3fs", (12, 11, 9), "random", 1, "3", [(5, 5, 4), (0, 0, 0), (11, 10, 8)]),
+    ("rand_5fs", (12, 11, 9), "random", 2, "5", [(6, 2, 8), (0, 10, 0)]),
+    ("rand_818", (12, 11, 9), "random", 3, "818", [(5, 5, 4), (11, 0, 8)]),
+    ("const_818", (20, 17, 13), "constant", 0, "818", [(10, 8, 12), (12, 9, 11), (0, 0, 0)]),
+    ("hetero_818", (33, 25, 40), "hetero", 5, "818", [(16, 12, 39), (8, 8, 0), (32, 24, 39)]),
+    ("contrast_5fs", (24, 24, 35), "contrast", 6, "5", [(3, 20, 17), (23, 23, 34)]),
+    ("tileedge_818", (17, 16, 33), "random", 7, "818", [(8, 8, 32), (16, 15, 31), (7, 8, 0)]),
+]
+
+
+def field(kind, dims, seed):
+    if kind == "random":
+        return W.random_field(dims, seed)
+    if kind == "constant":
+        return W.constant_field(dims, 0.25)
+    if kind == "hetero":
+        return W.heterogeneous_field(dims, seed)
+    if kind == "contrast":
+        return W.contrast_field(dims, seed)
+    raise ValueError(kind)
+
+
+def small():
+    out = {}
+    meta = []
+    for name, dims, kind, seed, star, starts in SMALL:
+        v = field(kind, dims, seed)
+        off = W.star(star)
+        for si, st in enumerate(starts):
+            tt, sweeps = oracle.ref_solve(v, off, st)
+            out[f"{name}__{si}"] = tt
+            meta.append(dict(case=name, idx=si, dims=dims, kind=kind, seed=seed, star=star, start=st, ref_sweeps=sweeps))
+            print(name, st, "sweeps", sweeps)
+        out[f"{name}__v_sha"] = np.frombuffer(hashlib.sha256(v.tobytes()).digest(), np.uint8)
+    out["meta_json"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
+    np.savez_compressed(GOLD / "small_cases.npz", **out)
+
+
+def _full_one(job):
+    label, kind, seed, star, start = job
+    v = field(kind, (241, 241, 51), seed)
+    t0 = time.time()
+    tt, sweeps = oracle.ref_solve(v, W.star(star), start)
+    flat = tt.ravel()
+    return dict(label=label, kind=kind, seed=seed, star=star, start=list(map(int, start)), ref_sweeps=sweeps,
+                seconds=round(time.time() - t0, 1), v_sha256=hashlib.sha256(v.tobytes()).hexdigest(),
+                tt_sha256=hashlib.sha256(tt.tobytes()).hexdigest(), sample_stride=4999,
+                sample_bits=[int(x) for x in flat[::4999].view(np.uint32)])
+
+
+def full():
+    jobs = [("config1_const_3fs", "constant", 0, "3", tuple(W.starts(1)[0]))]
+    for s, st in enumerate(W.starts(4)):
+        jobs.append((f"config2_hetero_818_src{s}", "hetero", 7, "818", tuple(st)))
+    with mp.Pool(len(jobs)) as pool:
+        res = pool.map(_full_one, jobs)
+    (GOLD / "full_241.json").write_text(json.dumps(res, indent=1))
+    for r in res:
+        print(r["label"], r["ref_sweeps"], r["seconds"], r["tt_sha256"][:16])
+
+
+if __name__ == "__main__":
+    {"small": small, "full": full}[sys.argv[1]]()

@@ -1,0 +1,71 @@
+// device_types.h -- structs shared between the host solver and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+
+namespace sweeptt {
+
+// ---- tile shape of the tiled kernel -------------------------------------------------
+// Interior tile TX x TY x TZ nodes; each thread owns KZ consecutive z nodes of one (x,y)
+// column (register window along the fastest axis).  256 threads per CTA.
+constexpr int TX = 8, TY = 8, TZ = 32, KZ = 8;
+constexpr int ZHALO = 8;                 // z halo staged on both sides (16-byte aligned)
+constexpr int SZD = TZ + 2 * ZHALO + 4;  // smem/TMA row length: 52 floats; 52/4 = 13 is odd,
+                                         // which makes the quarter-warp LDS.128 conflict-free
+constexpr int WIN = KZ + 2 * ZHALO;      // 24-float register window per (i,j) column
+constexpr int TILE_THREADS = TX * TY * (TZ / KZ);
+
+// ---- padded device float box ----------------------------------------------------------
+// Logical node (x,y,z) lives at padded index ((x+AX)*py + (y+AY))*pz + (z+AZ).
+// Apron: slowness = +INF (makes every edge touching it infinitely slow, which reproduces the
+// reference's bounds `continue`, serial_new/sweep-tt-multistart.c:210-214, with no test in
+// the inner loop), travel time = +INF.
+constexpr int AX = 7, AY = 7, AZ = ZHALO;
+
+struct BoxGeom {
+  int nx, ny, nz;      // logical dims
+  int px, py, pz;      // padded dims
+  int ntx, nty, ntz;   // tiles per axis
+  long long sx;        // py*pz
+  long long vol;       // px*py*pz floats per box
+};
+
+// ---- device-resident convergence state --------------------------------------------------
+struct SolveState {
+  int round;                 // rounds completed so far
+  int last_changed_round;    // 1-based index of the last round that changed anything
+  int parity;                // which work list the next round reads
+  unsigned count[2];         // entries in each work list
+  unsigned cursor;           // work-stealing cursor of the running round
+  unsigned ticket;           // last-block-done ticket of the compaction kernel
+  unsigned long long tile_visits;
+  unsigned long long pulls;  // in-bounds pull evaluations executed
+  int max_rounds;            // 0 = unlimited; the graph WHILE loop stops here
+  int pad;
+};
+
+struct ColumnDev {
+  int soff;        // smem float offset of the column: i*SYD*SZD + j*SZD
+  unsigned kmask;  // bit (k + ZHALO) for every k present
+  int hd_begin;    // first half-distance in c_col_hd
+  unsigned gmask;  // which 4-float granules of the 24-float window the column touches
+};
+
+struct ExtraDev {
+  int i, j, k;
+  int soff;        // smem float offset i*SYD*SZD + j*SZD + k
+  float hd;
+  int guarded;
+  int pad0, pad1;
+};
+
+struct StarDev {   // star as the simple kernel / verifier read it (global memory)
+  int i, j, k;
+  float hd;
+  int guarded;
+};
+
+constexpr int MAX_COLUMNS = 256;
+constexpr int MAX_COL_HD = 4096;
+constexpr int MAX_EXTRA = 64;
+
+}  // namespace sweeptt

@@ -1,0 +1,554 @@
+// kernels.cu -- hand-written sm_100a kernels of the multi-start forward-star sweep.
+//
+// What is computed (arithmetic contract): for every node n != start
+//     tt[n] = min(tt[n], min over pull offsets o of  fl(fl(hd_o * fl(v_n + v_{n+o})) + tt[n+o]))
+// which is the pull form of the reference's two-sided relaxation
+// (serial_new/sweep-tt-multistart.c:216,222-249) with hd_o = d_o/2 (exact halving) and NO
+// fused multiply-add anywhere (__fmul_rn/__fadd_rn never contract; the file is also built
+// with -fmad=false).  Any fair relaxation order reaches the same fixed point bit-for-bit,
+// because fl(a+c) is monotone in a and travel times only ever decrease.
+//
+// Kernels
+//   relax_tiled<RXY>  persistent CTAs steal dirty tiles from a device work list; TMA
+//                     (cp.async.bulk.tensor) stages the tile's slowness and travel-time boxes
+//                     plus the star-radius halo into shared memory behind an mbarrier; each
+//                     thread owns KZ=8 consecutive z nodes and, per (i,j) column of the star,
+//                     pulls a 24-float register window of both arrays with LDS.128 and runs
+//                     the column's k offsets out of registers; changed tiles mark their 27
+//                     neighbours dirty; results leave as 128-bit stores.
+//   compact_dirty     turns the dirty flags into the next round's work list, advances the
+//                     device-resident round counter and feeds the CUDA-graph WHILE condition.
+//   relax_simple      one thread per node, global memory, explicit bounds tests: the
+//                     verification path and the fallback for stars wider than the halo.
+//   count_violations  the fixed-point invariant (testconvergence,
+//                     old/wavefront-openmp/wave-multistart.c:300-347) on the device.
+//   fill/pad/unpad/init_sources  the device float-box pool's utilities
+//                     (boxsetall/boxput, include/floatbox.h:176-199).
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+#include <limits>
+
+namespace sweeptt {
+
+// ---------------------------------------------------------------------------------------
+// constant memory: the forward star, column-grouped (cuda/cudasweep-tt-multistart.cu:74
+// keeps struct FS dc_fs[] in __constant__; here offsets are pre-resolved to smem offsets
+// and the distances are pre-halved)
+// ---------------------------------------------------------------------------------------
+__constant__ ColumnDev c_cols[MAX_COLUMNS];
+__constant__ float c_col_hd[MAX_COL_HD];
+__constant__ ExtraDev c_extra[MAX_EXTRA];
+
+cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
+                                  const ExtraDev* extra, int nextra, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  if (ncols > 0)
+    e = cudaMemcpyToSymbolAsync(c_cols, cols, sizeof(ColumnDev) * ncols, 0, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && nhd > 0)
+    e = cudaMemcpyToSymbolAsync(c_col_hd, col_hd, sizeof(float) * nhd, 0, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && nextra > 0)
+    e = cudaMemcpyToSymbolAsync(c_extra, extra, sizeof(ExtraDev) * nextra, 0, cudaMemcpyHostToDevice, stream);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// tiled relaxation kernel
+// ---------------------------------------------------------------------------------------
+template <int RXY>
+struct TileDims {
+  static constexpr int SXD = TX + 2 * RXY;
+  static constexpr int SYD = TY + 2 * RXY;
+  static constexpr int BOX_FLOATS = SXD * SYD * SZD;
+  static constexpr size_t SMEM = 2 * sizeof(float) * BOX_FLOATS + 1024;  // + alignment slack
+};
+
+template <int RXY>
+__global__ void __launch_bounds__(TILE_THREADS, (RXY == 7) ? 1 : 2)
+relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
+            const RelaxArgs a) {
+  using D = TileDims<RXY>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned carve-up: [slowness box][travel-time box]
+  float* sv = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  float* st = sv + D::BOX_FLOATS;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_tile;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  // warp -> (x half, z chunk); lane -> (x within half, y): a quarter-warp shares x and zc and
+  // spans 8 consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
+  const int zc = warp & 3;
+  const int x = ((warp >> 2) << 2) | (lane >> 3);
+  const int y = lane & 7;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  SolveState* S = a.st;
+  const int par = S->parity;
+  const unsigned cnt = S->count[par];
+  const unsigned* wl = a.worklist + (size_t)par * a.cap;
+  const int round = S->round;
+  const int ntiles = a.g.ntx * a.g.nty * a.g.ntz;
+
+  // smem float index of this thread's window start for the (0,0) column
+  const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD + zc * KZ;
+
+  for (uint32_t it = 0;; ++it) {
+    if (tid == 0) {
+      const unsigned i = atomicAdd(&S->cursor, 1u);
+      s_tile = (i < cnt) ? (int)wl[i] : -1;
+    }
+    __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile
+    const int tile = s_tile;
+    if (tile < 0) break;
+    const int s = tile / ntiles;
+    int tp = tile - s * ntiles;
+    const int tz = tp % a.g.ntz; tp /= a.g.ntz;
+    const int ty = tp % a.g.nty;
+    const int tx = tp / a.g.nty;
+    const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;  // logical coords of the tile interior
+
+    if (tid == 0) {
+      // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
+      mbar_expect_tx(&bar, 2u * sizeof(float) * D::BOX_FLOATS);
+      tma_load_3d(sv, &tm_slow, &bar, z0 + AZ - ZHALO, y0 + AY - RXY, x0 + AX - RXY);
+      tma_load_4d(st, &tm_tt, &bar, z0 + AZ - ZHALO, y0 + AY - RXY, x0 + AX - RXY, s);
+    }
+    mbar_wait(&bar, it & 1);
+
+    // whole-warp skip when this warp's nodes are all outside the grid
+    const bool warp_live = (x0 + ((warp >> 2) << 2) < a.g.nx) && (z0 + zc * KZ < a.g.nz);
+    int changed = 0;
+    if (warp_live) {
+      float vn[KZ], told[KZ], acc[KZ];
+      {
+        const float4 v0 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO);
+        const float4 v1 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4);
+        const float4 t0 = *reinterpret_cast<const float4*>(st + b0 + ZHALO);
+        const float4 t1 = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4);
+        vn[0] = v0.x; vn[1] = v0.y; vn[2] = v0.z; vn[3] = v0.w;
+        vn[4] = v1.x; vn[5] = v1.y; vn[6] = v1.z; vn[7] = v1.w;
+        told[0] = t0.x; told[1] = t0.y; told[2] = t0.z; told[3] = t0.w;
+        told[4] = t1.x; told[5] = t1.y; told[6] = t1.z; told[7] = t1.w;
+      }
+#pragma unroll
+      for (int k = 0; k < KZ; ++k) acc[k] = told[k];
+
+      // ---- main loop: one (i,j) column of the star per iteration ----
+      float W[WIN], T[WIN];  // register windows; granules a column does not touch keep stale
+                             // (finite-or-INF, never read) values from earlier columns
+#pragma unroll
+      for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
+      for (int c = 0; c < a.ncols; ++c) {
+        const ColumnDev col = c_cols[c];
+        const float* pv = sv + b0 + col.soff;
+        const float* pt = st + b0 + col.soff;
+#pragma unroll
+        for (int g = 0; g < WIN / 4; ++g) {
+          if (col.gmask & (1u << g)) {
+            const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * g);
+            const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * g);
+            W[4 * g] = wv.x; W[4 * g + 1] = wv.y; W[4 * g + 2] = wv.z; W[4 * g + 3] = wv.w;
+            T[4 * g] = wt.x; T[4 * g + 1] = wt.y; T[4 * g + 2] = wt.z; T[4 * g + 3] = wt.w;
+          }
+        }
+        int hi = col.hd_begin;
+#pragma unroll
+        for (int b = 0; b <= 2 * ZHALO; ++b) {  // k = b - ZHALO
+          if (col.kmask & (1u << b)) {
+            const float hd = c_col_hd[hi++];
+#pragma unroll
+            for (int k = 0; k < KZ; ++k) {
+              const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
+              acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
+            }
+          }
+        }
+      }
+
+      // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
+      //      serial_new/...c:219-221 with :160) and duplicates ----
+      const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
+      const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+      for (int e = 0; e < a.nextra; ++e) {
+        const ExtraDev ex = c_extra[e];
+        const float* pv = sv + b0 + ZHALO + ex.soff;
+        const float* pt = st + b0 + ZHALO + ex.soff;
+#pragma unroll
+        for (int k = 0; k < KZ; ++k) {
+          const bool bad = ex.guarded && (gx + ex.i == px) && (gy + ex.j == py) && (gz + k + ex.k == pz);
+          const float delay = __fmul_rn(ex.hd, __fadd_rn(vn[k], pv[k]));
+          const float cand = __fadd_rn(delay, pt[k]);
+          if (!bad) acc[k] = fminf(acc[k], cand);
+        }
+      }
+
+      // the start point itself is never relaxed (serial_new/...c:219-221)
+      if (gx == px && gy == py) {
+#pragma unroll
+        for (int k = 0; k < KZ; ++k)
+          if (gz + k == pz) acc[k] = told[k];
+      }
+
+#pragma unroll
+      for (int k = 0; k < KZ; ++k) changed |= (acc[k] < told[k]);
+      if (changed) {
+        float* out = a.tt + (size_t)s * a.g.vol + ((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ);
+        *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+
+    // block-wide "anything changed" (also the barrier that ends all smem reads of this tile)
+    const int any = __syncthreads_or(changed);
+    if (any && tid < 27) {
+      const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
+      const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
+      if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
+        a.dirty[(size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz] = 1;
+    }
+    if (tid == 32) {
+      const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
+      atomicAdd(&S->tile_visits, 1ull);
+      atomicAdd(&S->pulls, a.tile_pulls[tpos]);
+      if (any) atomicMax(&S->last_changed_round, round + 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// work-list compaction + device-resident round bookkeeping
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_dirty(const RelaxArgs a, unsigned long long cond) {
+  SolveState* S = a.st;
+  const int nxt = S->parity ^ 1;
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool set = (i < total) && a.dirty[i];
+  // warp-aggregated append
+  const unsigned ballot = __ballot_sync(0xffffffffu, set);
+  if (ballot) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ballot) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&S->count[nxt], (unsigned)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (set) {
+      a.worklist[(size_t)nxt * a.cap + base + __popc(ballot & ((1u << lane) - 1))] = (unsigned)i;
+      a.dirty[i] = 0;
+    }
+  }
+  // last block done: flip the lists and advance the round
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&S->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    S->ticket = 0;
+    S->cursor = 0;
+    S->count[nxt ^ 1] = 0;
+    S->parity = nxt;
+    S->round += 1;
+#if __CUDA_ARCH__ >= 900
+    if (cond) {
+      const bool more = (S->last_changed_round == S->round) && (S->max_rounds == 0 || S->round < S->max_rounds);
+      cudaGraphSetConditional((cudaGraphConditionalHandle)cond, more ? 1u : 0u);
+    }
+#endif
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// simple path: one thread per (node, source), global memory, explicit bounds tests
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float pull_min_global(const RelaxArgs& a, const float* __restrict__ tt, int x, int y,
+                                                 int z, const StarDev* __restrict__ star, int nstar, int px, int py,
+                                                 int pz, float cur) {
+  const size_t n = ((size_t)(x + AX) * a.g.py + (y + AY)) * a.g.pz + (z + AZ);
+  const float vn = a.slow[n];
+  float best = cur;
+  for (int l = 0; l < nstar; ++l) {
+    const StarDev o = star[l];
+    const int xo = x + o.i, yo = y + o.j, zo = z + o.k;
+    if ((unsigned)xo >= (unsigned)a.g.nx || (unsigned)yo >= (unsigned)a.g.ny || (unsigned)zo >= (unsigned)a.g.nz)
+      continue;
+    if (o.guarded && xo == px && yo == py && zo == pz) continue;
+    const size_t m = ((size_t)(xo + AX) * a.g.py + (yo + AY)) * a.g.pz + (zo + AZ);
+    const float delay = __fmul_rn(o.hd, __fadd_rn(vn, a.slow[m]));
+    best = fminf(best, __fadd_rn(delay, tt[m]));
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(128) relax_simple(const RelaxArgs a, const StarDev* __restrict__ star, int nstar,
+                                                    unsigned long long pulls_per_round) {
+  // z fastest across threads -> coalesced
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y % a.g.ny, x = blockIdx.y / a.g.ny;
+  const int s = blockIdx.z;
+  int changed = 0;
+  if (z < a.g.nz) {
+    const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+    float* tt = a.tt + (size_t)s * a.g.vol;
+    if (!(x == px && y == py && z == pz)) {
+      const size_t n = ((size_t)(x + AX) * a.g.py + (y + AY)) * a.g.pz + (z + AZ);
+      const float cur = tt[n];
+      const float best = pull_min_global(a, tt, x, y, z, star, nstar, px, py, pz, cur);
+      if (best < cur) {
+        tt[n] = best;  // chaotic in-place update: any mix of old/new neighbours is a valid relaxation
+        changed = 1;
+      }
+    }
+  }
+  if (__syncthreads_or(changed) && threadIdx.x == 0) atomicMax(&a.st->last_changed_round, a.st->round + 1);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&a.st->pulls, pulls_per_round);
+}
+
+__global__ void advance_simple(SolveState* S, unsigned long long cond) {
+  S->round += 1;
+#if __CUDA_ARCH__ >= 900
+  if (cond) {
+    const bool more = (S->last_changed_round == S->round) && (S->max_rounds == 0 || S->round < S->max_rounds);
+    cudaGraphSetConditional((cudaGraphConditionalHandle)cond, more ? 1u : 0u);
+  }
+#endif
+}
+
+__global__ void __launch_bounds__(128) count_violations_kernel(const RelaxArgs a, int s,
+                                                               const StarDev* __restrict__ star, int nstar,
+                                                               unsigned long long* out) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y % a.g.ny, x = blockIdx.y / a.g.ny;
+  unsigned bad = 0;
+  if (z < a.g.nz) {
+    const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+    const float* tt = a.tt + (size_t)s * a.g.vol;
+    if (!(x == px && y == py && z == pz)) {
+      const size_t n = ((size_t)(x + AX) * a.g.py + (y + AY)) * a.g.pz + (z + AZ);
+      const float vn = a.slow[n], cur = tt[n];
+      for (int l = 0; l < nstar; ++l) {
+        const StarDev o = star[l];
+        const int xo = x + o.i, yo = y + o.j, zo = z + o.k;
+        if ((unsigned)xo >= (unsigned)a.g.nx || (unsigned)yo >= (unsigned)a.g.ny ||
+            (unsigned)zo >= (unsigned)a.g.nz)
+          continue;
+        if (o.guarded && xo == px && yo == py && zo == pz) continue;
+        const size_t m = ((size_t)(xo + AX) * a.g.py + (yo + AY)) * a.g.pz + (zo + AZ);
+        const float cand = __fadd_rn(__fmul_rn(o.hd, __fadd_rn(vn, a.slow[m])), tt[m]);
+        bad += (cand < cur);
+      }
+    } else if (tt[((size_t)(x + AX) * a.g.py + (y + AY)) * a.g.pz + (z + AZ)] != 0.0f) {
+      bad = 1;
+    }
+  }
+  for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+// ---------------------------------------------------------------------------------------
+// float-box utilities
+// ---------------------------------------------------------------------------------------
+__global__ void fill_kernel(float4* p, long long n4, float value) {
+  const float4 v = make_float4(value, value, value, value);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void pad_kernel(const float* __restrict__ dense, float* __restrict__ padded, BoxGeom g) {
+  const long long vol = (long long)g.nx * g.ny * g.nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % g.nz);
+    const long long r = i / g.nz;
+    const int y = (int)(r % g.ny), x = (int)(r / g.ny);
+    padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)] = dense[i];
+  }
+}
+__global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict__ dense, BoxGeom g) {
+  const long long vol = (long long)g.nx * g.ny * g.nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % g.nz);
+    const long long r = i / g.nz;
+    const int y = (int)(r % g.ny), x = (int)(r / g.ny);
+    dense[i] = padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)];
+  }
+}
+// one block per source: tt[start] = 0 and the 27 tiles around the start's tile go on list 0
+__global__ void init_sources_kernel(const RelaxArgs a) {
+  const int s = blockIdx.x;
+  const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+  if (threadIdx.x == 31)
+    a.tt[(size_t)s * a.g.vol + ((size_t)(px + AX) * a.g.py + (py + AY)) * a.g.pz + (pz + AZ)] = 0.0f;
+  if (threadIdx.x < 27) {
+    const int tid = threadIdx.x;
+    const int ux = px / TX + tid / 9 - 1, uy = py / TY + (tid / 3) % 3 - 1, uz = pz / TZ + tid % 3 - 1;
+    if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
+      const unsigned ntiles = a.g.ntx * a.g.nty * a.g.ntz;
+      const unsigned pos = atomicAdd(&a.st->count[0], 1u);
+      a.worklist[pos] = s * ntiles + (ux * a.g.nty + uy) * a.g.ntz + uz;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+int tiled_variant_for_radius(int r) {
+  if (r <= 2) return 2;
+  if (r <= 4) return 4;
+  if (r <= 7) return 7;
+  return 0;
+}
+void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd) {
+  *sxd = TX + 2 * rxy; *syd = TY + 2 * rxy; *szd = SZD;
+}
+
+template <int RXY>
+static cudaError_t prepare_variant(int device, TiledLaunch* out) {
+  using D = TileDims<RXY>;
+  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0, sms = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY>, TILE_THREADS, D::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  out->rxy = RXY;
+  out->grid = per_sm * sms;
+  out->smem_bytes = D::SMEM;
+  return cudaSuccess;
+}
+cudaError_t tiled_prepare(int rxy, int device, TiledLaunch* out) {
+  switch (rxy) {
+    case 2: return prepare_variant<2>(device, out);
+    case 4: return prepare_variant<4>(device, out);
+    case 7: return prepare_variant<7>(device, out);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                               const RelaxArgs& a, cudaStream_t stream) {
+  switch (tl.rxy) {
+    case 2: relax_tiled<2><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 4: relax_tiled<4><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 7: relax_tiled<7><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream) {
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  compact_dirty<<<blocks, 256, 0, stream>>>(a, cond);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_relax_simple(const RelaxArgs& a, const StarDev* star, int nstar,
+                                unsigned long long pulls_per_round, cudaStream_t stream) {
+  dim3 grid((a.g.nz + 127) / 128, a.g.nx * a.g.ny, a.nsrc);
+  relax_simple<<<grid, 128, 0, stream>>>(a, star, nstar, pulls_per_round);
+  return cudaGetLastError();
+}
+cudaError_t launch_advance_simple(SolveState* st, unsigned long long cond, cudaStream_t stream) {
+  advance_simple<<<1, 1, 0, stream>>>(st, cond);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_violations(const RelaxArgs& a, int source, const StarDev* star, int nstar,
+                                    unsigned long long* out, cudaStream_t stream) {
+  dim3 grid((a.g.nz + 127) / 128, a.g.nx * a.g.ny, 1);
+  count_violations_kernel<<<grid, 128, 0, stream>>>(a, source, star, nstar, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(float* p, long long n, float value, cudaStream_t stream) {
+  // boxes are multiples of 4 floats and 16-byte aligned by construction
+  fill_kernel<<<1184, 256, 0, stream>>>(reinterpret_cast<float4*>(p), n / 4, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_pad_box(const float* dense, float* padded, BoxGeom g, cudaStream_t stream) {
+  pad_kernel<<<1184, 256, 0, stream>>>(dense, padded, g);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpad_box(const float* padded, float* dense, BoxGeom g, cudaStream_t stream) {
+  unpad_kernel<<<1184, 256, 0, stream>>>(padded, dense, g);
+  return cudaGetLastError();
+}
+__global__ void init_state_kernel(SolveState* S, int max_rounds) {
+  SolveState z = {};
+  z.max_rounds = max_rounds;
+  *S = z;
+}
+cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {
+  init_state_kernel<<<1, 1, 0, stream>>>(a.st, max_rounds);
+  cudaError_t e = launch_fill(a.tt, (long long)a.nsrc * a.g.vol, std::numeric_limits<float>::infinity(), stream);
+  if (e != cudaSuccess) return e;
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  e = cudaMemsetAsync(a.dirty, 0, total, stream);
+  if (e != cudaSuccess) return e;
+  init_sources_kernel<<<a.nsrc, 32, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace sweeptt

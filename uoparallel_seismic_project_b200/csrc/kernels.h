@@ -1,0 +1,63 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace sweeptt {
+
+struct TiledLaunch {
+  int rxy;                   // halo template: 2, 4 or 7
+  int grid;                  // persistent CTAs
+  size_t smem_bytes;
+};
+
+// Shared-memory halo variant for a star with max(|i|,|j|) = r (2, 4 or 7), or 0 if none fits.
+int tiled_variant_for_radius(int r);
+// smem row/plane pitches of a variant (host needs them to precompute column offsets).
+void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd);
+// Occupancy-derived persistent grid + opt-in shared memory; returns cudaSuccess or an error.
+cudaError_t tiled_prepare(int rxy, int device, TiledLaunch* out);
+
+// Upload the column tables into __constant__ memory (stream ordered).
+cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
+                                  const ExtraDev* extra, int nextra, cudaStream_t stream);
+
+struct RelaxArgs {
+  BoxGeom g;
+  const float* slow;           // padded slowness box
+  float* tt;                   // nsrc padded travel-time boxes, contiguous
+  int nsrc;
+  const int* src_xyz;          // 3 ints per source (logical coords)
+  SolveState* st;
+  unsigned* worklist;          // 2 * cap entries
+  unsigned cap;
+  unsigned char* dirty;        // nsrc * ntiles flags (marks for the next round)
+  const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
+  int ncols, nextra;
+};
+
+cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow,
+                               const CUtensorMap& tm_tt, const RelaxArgs& a, cudaStream_t stream);
+// Scans the dirty flags into the next work list, flips parity, advances the round and (when
+// cond != 0) sets the CUDA-graph WHILE condition to "changed in the round just finished".
+cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream);
+
+// Simple (verification / fallback) path: one thread per node and source, global memory.
+cudaError_t launch_relax_simple(const RelaxArgs& a, const StarDev* star, int nstar,
+                                unsigned long long pulls_per_round, cudaStream_t stream);
+cudaError_t launch_advance_simple(SolveState* st, unsigned long long cond, cudaStream_t stream);
+
+// Fixed-point verifier.
+cudaError_t launch_count_violations(const RelaxArgs& a, int source, const StarDev* star, int nstar,
+                                    unsigned long long* out, cudaStream_t stream);
+
+// Box utilities (device float-box pool).
+cudaError_t launch_fill(float* p, long long n, float value, cudaStream_t stream);
+cudaError_t launch_pad_box(const float* dense, float* padded, BoxGeom g, cudaStream_t stream);
+cudaError_t launch_unpad_box(const float* padded, float* dense, BoxGeom g, cudaStream_t stream);
+// tt := INF everywhere, 0 at each start; state, flags and the first work list reset.
+cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream);
+
+}  // namespace sweeptt

@@ -1,0 +1,51 @@
+// pullstar.h -- host-side edge-set analysis shared by the solver and the C ABI.
+//
+// The reference relaxes BOTH directions of an edge from the sweep centre
+// (serial_new/sweep-tt-multistart.c:222-249) but (quirk 1) never uses the last star
+// entry as a centre offset (:160 passes starsize-1) and (quirk 2) skips every visit whose
+// centre is the start point (:219-221).  For owner-computes GPU kernels we need the
+// equivalent PULL form: for node n, which neighbours m = n+o may lower tt[n], with which
+// half-distance, and which of those pulls are invalid when m is the start point.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/sweeptt.h"
+
+namespace sweeptt {
+
+struct PullOffset {
+  int i, j, k;   // m = n + (i,j,k)
+  float hd;      // 0.5f * d   (halving is exact, so hd*(v_n+v_m) == d*(v_n+v_m)/2.0)
+  int guarded;   // 1: only supplied by "centre m relaxes neighbour n" => invalid when m == start
+};
+
+// One (i,j) column of plain (unguarded) pulls for the tiled kernel: the k offsets present
+// are a bit mask over k in [-KHALO, +KHALO]; hd values follow in ascending-k order.
+struct PullColumn {
+  int i, j;
+  uint32_t kmask;   // bit (k + KHALO)
+  int hd_begin;     // index of the first hd of this column in PullStar::col_hd
+};
+
+constexpr int KHALO = 8;      // z halo kept in shared memory / padding (16-byte aligned)
+constexpr int RXY_MAX = 7;    // largest |i|,|j| the tiled kernel's shared-memory halo holds
+
+struct PullStar {
+  std::vector<PullOffset> all;       // every pull (plain first, then guarded/extra)
+  std::vector<PullColumn> columns;   // plain pulls grouped by (i,j), sorted by (i,j)
+  std::vector<float> col_hd;         // hd of the column-grouped pulls
+  std::vector<PullOffset> extra;     // pulls handled one at a time (guarded or duplicates)
+  int rx = 0, ry = 0, rz = 0;        // max |i|, |j|, |k| over all pulls
+  bool fits_tiled() const { return rx <= RXY_MAX && ry <= RXY_MAX && rz <= KHALO; }
+};
+
+// star_used <= 0 means starsize-1 (what the reference passes).
+PullStar build_pull_star(const FS* fs, int starsize, int star_used);
+
+// In-bounds pull evaluations of one round over the sub-box [x0,x1)x[y0,y1)x[z0,z1) of an
+// nx*ny*nz grid (neighbour anywhere in the grid).
+long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1, int y0, int y1,
+                      int z0, int z1);
+
+}  // namespace sweeptt

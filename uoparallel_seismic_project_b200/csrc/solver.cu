@@ -1,0 +1,893 @@
+// solver.cu -- host side of the C ABI (include/sweeptt.h): device float-box pool, star
+// tables, the device-resident convergence loop, the multi-start dispatcher.
+//
+// Replaces the host orchestration of cudaRun (cuda/cudasweep-tt-multistart.cu:227-410) and
+// the serial convergence loop (serial_new/sweep-tt-multistart.c:150-170).  Differences by
+// design: no per-sweep host round trip (CUDA-graph WHILE node, or K rounds per poll), all
+// sources relaxed concurrently from one work list, sources sharded over GPUs instead of the
+// reference's star splitting.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sweeptt.h"
+#include "kernels.h"
+#include "pullstar.h"
+
+using namespace sweeptt;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+namespace sweeptt {
+// records the message for sweeptt_last_error() and returns 0 (= failure in this ABI)
+int set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 0;
+}
+}  // namespace sweeptt
+#define fail sweeptt::set_error
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* sweeptt_last_error(void) { return g_err.c_str(); }
+extern "C" const char* sweeptt_version(void) { return "sweeptt-b200 0.1 (sm_100a)"; }
+
+extern "C" int sweeptt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int sweeptt_device_info(int device, char* name, int name_len, int* sm_count, int* clock_khz,
+                                   size_t* smem_optin) {
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (name && name_len > 0) snprintf(name, name_len, "%s", p.name);
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (clock_khz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    *clock_khz = khz;
+  }
+  if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+  return 1;
+}
+
+extern "C" void sweeptt_star_fill_distances(struct FS* fs, int starsize, float delta) {
+  // serial_new/sweep-tt-multistart.c:122,127: sqrt in double on an int, stored to float, times delta
+  for (int l = 0; l < starsize; ++l) {
+    float d = (float)std::sqrt((double)(fs[l].i * fs[l].i + fs[l].j * fs[l].j + fs[l].k * fs[l].k));
+    fs[l].d = delta * d;
+  }
+}
+
+extern "C" int sweeptt_build_pull_star(const struct FS* fs, int starsize, int star_used, int32_t* ijk_out,
+                                       float* half_d_out, int32_t* guard_out, int capacity) {
+  if (!fs || starsize <= 0) return -1;
+  PullStar ps = build_pull_star(fs, starsize, star_used);
+  const int n = (int)ps.all.size();
+  if (capacity < n && (ijk_out || half_d_out || guard_out)) return -1;
+  for (int l = 0; l < n; ++l) {
+    if (ijk_out) { ijk_out[3 * l] = ps.all[l].i; ijk_out[3 * l + 1] = ps.all[l].j; ijk_out[3 * l + 2] = ps.all[l].k; }
+    if (half_d_out) half_d_out[l] = ps.all[l].hd;
+    if (guard_out) guard_out[l] = ps.all[l].guarded;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+struct sweeptt_ctx {
+  sweeptt_opts opts{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+
+  BoxGeom g{};
+  bool have_model = false, have_star = false, have_sources = false;
+  float* d_slow = nullptr;
+  float* d_tt = nullptr;
+  int tt_cap = 0;  // boxes allocated in the pool
+  int nsrc = 0;
+  std::vector<int> src_xyz;
+  int* d_src = nullptr;
+  int src_cap = 0;
+  SolveState* d_state = nullptr;
+  SolveState* h_state = nullptr;  // pinned mirror
+  unsigned* d_worklist = nullptr;
+  unsigned char* d_dirty = nullptr;
+  size_t tiles_cap = 0;  // nsrc*ntiles the lists/flags were sized for
+  unsigned long long* d_tile_pulls = nullptr;
+  unsigned long long* d_viol = nullptr;
+  float* d_stage = nullptr;  // dense staging box for pad/unpad
+  size_t stage_floats = 0;
+  size_t pool_bytes = 0;
+
+  std::vector<FS> fs;
+  PullStar star;
+  StarDev* d_star = nullptr;
+  int nstar = 0;
+  long long pulls_per_round = 0;
+
+  int kernel_used = 0;
+  TiledLaunch tl{};
+  CUtensorMap tm_slow{}, tm_tt{};
+  bool maps_valid = false;
+  int consts_rxy = -1;  // variant the __constant__ tables were built for
+
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+
+  std::vector<cudaEvent_t> prof_events;
+};
+
+// the __constant__ star tables are per-device module state: remember which context owns them
+static std::mutex g_const_mu;
+static std::map<int, sweeptt_ctx*> g_const_owner;
+
+static void invalidate_graph(sweeptt_ctx* c) {
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr;
+  c->graph_valid = false;
+}
+
+static int dev_alloc(sweeptt_ctx* c, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes));
+  c->pool_bytes += bytes;
+  return 1;
+}
+static void dev_free(sweeptt_ctx* c, void* p, size_t bytes) {
+  if (p) {
+    cudaFree(p);
+    c->pool_bytes -= std::min(bytes, c->pool_bytes);
+  }
+}
+
+extern "C" sweeptt_ctx* sweeptt_create(const sweeptt_opts* opts) {
+  int ndev = sweeptt_device_count();
+  if (ndev <= 0) {
+    fail("no CUDA device available: the sweep has no CPU fallback");
+    return nullptr;
+  }
+  auto* c = new sweeptt_ctx();
+  if (opts) std::memcpy(&c->opts, opts, std::min<size_t>(sizeof(sweeptt_opts), opts->struct_size > 0 ? opts->struct_size : sizeof(sweeptt_opts)));
+  int dev = c->opts.device;
+  if (dev < 0) cudaGetDevice(&dev);
+  if (dev >= ndev) {
+    fail("device %d out of range (have %d)", dev, ndev);
+    delete c;
+    return nullptr;
+  }
+  c->device = dev;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    fail("cannot select device %d", dev);
+    delete c;
+    return nullptr;
+  }
+  if (prop.major < 10) {
+    fail("device %d (%s) is sm_%d%d; this library ships sm_100a kernels only", dev, prop.name, prop.major, prop.minor);
+    delete c;
+    return nullptr;
+  }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  c->own_stream = true;
+  ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
+       cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState)) == cudaSuccess &&
+       cudaMallocHost(&c->h_state, sizeof(SolveState)) == cudaSuccess &&
+       cudaMalloc(&c->d_viol, sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) {
+    fail("context setup failed on device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+    sweeptt_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    auto it = g_const_owner.find(c->device);
+    if (it != g_const_owner.end() && it->second == c) g_const_owner.erase(it);
+  }
+  invalidate_graph(c);
+  for (auto e : c->prof_events) cudaEventDestroy(e);
+  cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
+  cudaFree(c->d_worklist); cudaFree(c->d_dirty); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
+  cudaFree(c->d_stage); cudaFree(c->d_star);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev3) cudaEventDestroy(c->ev3);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int sweeptt_set_stream(sweeptt_ctx* c, void* cuda_stream) {
+  if (!c) return fail("null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->own_stream = false;
+  invalidate_graph(c);
+  return 1;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int ensure_stage(sweeptt_ctx* c, size_t floats) {
+  if (c->stage_floats >= floats) return 1;
+  dev_free(c, c->d_stage, c->stage_floats * 4);
+  c->d_stage = nullptr; c->stage_floats = 0;
+  if (!dev_alloc(c, (void**)&c->d_stage, floats * 4)) return 0;
+  c->stage_floats = floats;
+  return 1;
+}
+
+static int build_tile_pulls(sweeptt_ctx* c);
+static int build_maps(sweeptt_ctx* c);
+static int choose_kernel(sweeptt_ctx* c);
+
+extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, int ny, int nz) {
+  if (!c || !slowness) return fail("sweeptt_set_model: null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sweeptt_set_model: bad dimensions %d x %d x %d", nx, ny, nz);
+  CK(cudaSetDevice(c->device));
+  BoxGeom g{};
+  g.nx = nx; g.ny = ny; g.nz = nz;
+  g.ntx = (nx + TX - 1) / TX; g.nty = (ny + TY - 1) / TY; g.ntz = (nz + TZ - 1) / TZ;
+  g.px = AX + g.ntx * TX + RXY_MAX;
+  g.py = AY + g.nty * TY + RXY_MAX;
+  g.pz = AZ + g.ntz * TZ + ZHALO + 4;  // +4: the staged row is SZD = TZ+2*ZHALO+4 floats long
+  g.sx = (long long)g.py * g.pz;
+  g.vol = (long long)g.px * g.sx;
+  if ((long long)g.ntx * g.nty * g.ntz > 0x7fffffffLL) return fail("grid too large for 32-bit tile ids");
+  const bool same = c->have_model && c->g.px == g.px && c->g.py == g.py && c->g.pz == g.pz;
+  if (!same) {
+    CK(cudaStreamSynchronize(c->stream));
+    dev_free(c, c->d_slow, (size_t)c->g.vol * 4);
+    c->d_slow = nullptr;
+    dev_free(c, c->d_tt, (size_t)c->g.vol * 4 * c->tt_cap);
+    c->d_tt = nullptr; c->tt_cap = 0; c->have_sources = false;
+    if (!dev_alloc(c, (void**)&c->d_slow, (size_t)g.vol * 4)) return 0;
+    c->maps_valid = false;
+    invalidate_graph(c);
+  }
+  c->g = g;
+  const size_t dense = (size_t)nx * ny * nz;
+  if (!ensure_stage(c, dense)) return 0;
+  CK(launch_fill(c->d_slow, g.vol, std::numeric_limits<float>::infinity(), c->stream));
+  CK(cudaMemcpyAsync(c->d_stage, slowness, dense * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(launch_pad_box(c->d_stage, c->d_slow, g, c->stream));
+  c->have_model = true;
+  if (c->have_star && !build_tile_pulls(c)) return 0;
+  return 1;
+}
+
+static int build_tile_pulls(sweeptt_ctx* c) {
+  // per tile position: in-bounds pulls of one visit.  Memoised on the per-axis clipping
+  // class so only O(5^3) distinct products are evaluated.
+  const BoxGeom& g = c->g;
+  auto axis_classes = [&](int nt, int T, int n, int r, std::vector<int>& cls, std::vector<std::pair<int, int>>& rep) {
+    cls.resize(nt);
+    std::map<std::vector<int>, int> seen;
+    for (int t = 0; t < nt; ++t) {
+      const int lo = t * T, hi = std::min(n, lo + T);
+      std::vector<int> sig;
+      for (int o = -r; o <= r; ++o) sig.push_back(std::max(0, std::min(hi, n - o) - std::max(lo, -o)));
+      auto it = seen.find(sig);
+      if (it == seen.end()) {
+        it = seen.emplace(sig, (int)rep.size()).first;
+        rep.push_back({lo, hi});
+      }
+      cls[t] = it->second;
+    }
+  };
+  std::vector<int> cx, cy, cz;
+  std::vector<std::pair<int, int>> rx, ry, rz;
+  axis_classes(g.ntx, TX, g.nx, c->star.rx, cx, rx);
+  axis_classes(g.nty, TY, g.ny, c->star.ry, cy, ry);
+  axis_classes(g.ntz, TZ, g.nz, c->star.rz, cz, rz);
+  std::map<std::tuple<int, int, int>, unsigned long long> memo;
+  std::vector<unsigned long long> table((size_t)g.ntx * g.nty * g.ntz);
+  for (int tx = 0; tx < g.ntx; ++tx)
+    for (int ty = 0; ty < g.nty; ++ty)
+      for (int tz = 0; tz < g.ntz; ++tz) {
+        auto key = std::make_tuple(cx[tx], cy[ty], cz[tz]);
+        auto it = memo.find(key);
+        if (it == memo.end()) {
+          const auto& X = rx[cx[tx]]; const auto& Y = ry[cy[ty]]; const auto& Z = rz[cz[tz]];
+          it = memo.emplace(key, (unsigned long long)count_pulls(c->star, g.nx, g.ny, g.nz, X.first, X.second, Y.first,
+                                                                  Y.second, Z.first, Z.second)).first;
+        }
+        table[((size_t)tx * g.nty + ty) * g.ntz + tz] = it->second;
+      }
+  c->pulls_per_round = count_pulls(c->star, g.nx, g.ny, g.nz, 0, g.nx, 0, g.ny, 0, g.nz);
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_tile_pulls);
+  c->d_tile_pulls = nullptr;
+  CK(cudaMalloc(&c->d_tile_pulls, table.size() * 8));
+  CK(cudaMemcpy(c->d_tile_pulls, table.data(), table.size() * 8, cudaMemcpyHostToDevice));
+  return 1;
+}
+
+extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsize) {
+  if (!c || !fs) return fail("sweeptt_set_star: null argument");
+  if (starsize < 2) return fail("sweeptt_set_star: a forward star needs at least 2 entries (the last one is unused)");
+  CK(cudaSetDevice(c->device));
+  c->fs.assign(fs, fs + starsize);
+  c->star = build_pull_star(fs, starsize, c->opts.star_used);
+  if (c->star.all.empty()) return fail("sweeptt_set_star: the star has no usable offsets");
+  std::vector<StarDev> sd(c->star.all.size());
+  for (size_t l = 0; l < sd.size(); ++l) {
+    const PullOffset& p = c->star.all[l];
+    sd[l] = StarDev{p.i, p.j, p.k, p.hd, p.guarded};
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_star);
+  c->d_star = nullptr;
+  CK(cudaMalloc(&c->d_star, sd.size() * sizeof(StarDev)));
+  CK(cudaMemcpy(c->d_star, sd.data(), sd.size() * sizeof(StarDev), cudaMemcpyHostToDevice));
+  c->nstar = (int)sd.size();
+  c->have_star = true;
+  c->consts_rxy = -1;
+  invalidate_graph(c);
+  if (!choose_kernel(c)) return 0;
+  if (c->have_model && !build_tile_pulls(c)) return 0;
+  return 1;
+}
+
+static int choose_kernel(sweeptt_ctx* c) {
+  const int want = c->opts.kernel;
+  int rxy = 0;
+  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() <= MAX_COLUMNS &&
+                    (int)c->star.col_hd.size() <= MAX_COL_HD && (int)c->star.extra.size() <= MAX_EXTRA;
+  if (fits) rxy = tiled_variant_for_radius(std::max(c->star.rx, c->star.ry));
+  if (want == SWEEPTT_KERNEL_SIMPLE || (want == SWEEPTT_KERNEL_AUTO && rxy == 0)) {
+    c->kernel_used = SWEEPTT_KERNEL_SIMPLE;
+    return 1;
+  }
+  if (rxy == 0)
+    return fail("the tiled kernel holds |i|,|j| <= %d, |k| <= %d and <= %d guarded offsets; this star needs (%d,%d,%d) / %d",
+                RXY_MAX, KHALO, MAX_EXTRA, c->star.rx, c->star.ry, c->star.rz, (int)c->star.extra.size());
+  const char* force = getenv("SWEEPTT_FORCE_RXY");  // testing: run a small star in a wider halo variant
+  if (force && atoi(force) >= rxy) rxy = tiled_variant_for_radius(atoi(force));
+  CK(tiled_prepare(rxy, c->device, &c->tl));
+  c->kernel_used = SWEEPTT_KERNEL_TILED;
+  c->maps_valid = false;
+  return 1;
+}
+
+static int upload_constants(sweeptt_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  auto it = g_const_owner.find(c->device);
+  if (it != g_const_owner.end() && it->second == c && c->consts_rxy == c->tl.rxy) return 1;
+  int sxd, syd, szd;
+  tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
+  std::vector<ColumnDev> cols(c->star.columns.size());
+  for (size_t i = 0; i < cols.size(); ++i) {
+    const PullColumn& pc = c->star.columns[i];
+    ColumnDev d;
+    d.soff = pc.i * syd * szd + pc.j * szd;
+    d.kmask = pc.kmask;
+    d.hd_begin = pc.hd_begin;
+    d.gmask = 0;
+    for (int b = 0; b <= 2 * ZHALO; ++b)
+      if (pc.kmask & (1u << b))
+        for (int k = 0; k < KZ; ++k) d.gmask |= 1u << ((k + b) / 4);
+    cols[i] = d;
+  }
+  std::vector<ExtraDev> ex(c->star.extra.size());
+  for (size_t i = 0; i < ex.size(); ++i) {
+    const PullOffset& p = c->star.extra[i];
+    ex[i] = ExtraDev{p.i, p.j, p.k, p.i * syd * szd + p.j * szd + p.k, p.hd, p.guarded, 0, 0};
+  }
+  // a different context may still be running with the old tables on another stream
+  if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
+  CK(upload_star_constants(cols.data(), (int)cols.size(), c->star.col_hd.data(), (int)c->star.col_hd.size(), ex.data(),
+                           (int)ex.size(), c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // host vectors die here
+  g_const_owner[c->device] = c;
+  c->consts_rxy = c->tl.rxy;
+  return 1;
+}
+
+static int build_maps(sweeptt_ctx* c) {
+  if (c->maps_valid) return 1;
+  auto enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from this driver");
+  const BoxGeom& g = c->g;
+  int sxd, syd, szd;
+  tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)g.px};
+    cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.sx * 4};
+    cuuint32_t box[3] = {(cuuint32_t)szd, (cuuint32_t)syd, (cuuint32_t)sxd};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&c->tm_slow, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->d_slow, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(slowness) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)g.px, (cuuint64_t)std::max(1, c->tt_cap)};
+    cuuint64_t strides[3] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.sx * 4, (cuuint64_t)g.vol * 4};
+    cuuint32_t box[4] = {(cuuint32_t)szd, (cuuint32_t)syd, (cuuint32_t)sxd, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&c->tm_tt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_tt, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(travel times) failed: %d", (int)r);
+  }
+  c->maps_valid = true;
+  invalidate_graph(c);
+  return 1;
+}
+
+extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, int numstart) {
+  if (!c || !starts) return fail("sweeptt_set_sources: null argument");
+  if (!c->have_model) return fail("sweeptt_set_sources: set the model first");
+  if (numstart <= 0) return fail("sweeptt_set_sources: need at least one start point");
+  CK(cudaSetDevice(c->device));
+  const BoxGeom& g = c->g;
+  for (int s = 0; s < numstart; ++s)
+    if (starts[s].i < 0 || starts[s].i >= g.nx || starts[s].j < 0 || starts[s].j >= g.ny || starts[s].k < 0 ||
+        starts[s].k >= g.nz)
+      return fail("start point %d (%d,%d,%d) is outside the %d x %d x %d model", s, starts[s].i, starts[s].j,
+                  starts[s].k, g.nx, g.ny, g.nz);
+  CK(cudaStreamSynchronize(c->stream));
+  if (numstart > c->tt_cap) {  // grow the pool
+    dev_free(c, c->d_tt, (size_t)g.vol * 4 * c->tt_cap);
+    c->d_tt = nullptr; c->tt_cap = 0;
+    if (!dev_alloc(c, (void**)&c->d_tt, (size_t)g.vol * 4 * numstart)) return 0;
+    c->tt_cap = numstart;
+    c->maps_valid = false;
+    invalidate_graph(c);
+  }
+  if (numstart > c->src_cap) {
+    cudaFree(c->d_src);
+    c->d_src = nullptr;
+    CK(cudaMalloc(&c->d_src, sizeof(int) * 3 * numstart));
+    c->src_cap = numstart;
+    invalidate_graph(c);
+  }
+  const size_t ntiles = (size_t)g.ntx * g.nty * g.ntz;
+  if (ntiles * numstart > 0xfffffff0ull) return fail("too many tiles (%zu x %d sources) for 32-bit work-list entries", ntiles, numstart);
+  if (ntiles * numstart > c->tiles_cap) {
+    dev_free(c, c->d_worklist, c->tiles_cap * 8);
+    dev_free(c, c->d_dirty, c->tiles_cap);
+    c->d_worklist = nullptr; c->d_dirty = nullptr;
+    c->tiles_cap = ntiles * numstart;
+    if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 8)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_dirty, c->tiles_cap)) return 0;
+    invalidate_graph(c);
+  }
+  if (numstart != c->nsrc) invalidate_graph(c);
+  c->nsrc = numstart;
+  c->src_xyz.resize(3 * numstart);
+  for (int s = 0; s < numstart; ++s) {
+    c->src_xyz[3 * s] = starts[s].i; c->src_xyz[3 * s + 1] = starts[s].j; c->src_xyz[3 * s + 2] = starts[s].k;
+  }
+  CK(cudaMemcpy(c->d_src, c->src_xyz.data(), sizeof(int) * 3 * numstart, cudaMemcpyHostToDevice));
+  c->have_sources = true;
+  return 1;
+}
+
+static RelaxArgs make_args(sweeptt_ctx* c) {
+  RelaxArgs a{};
+  a.g = c->g;
+  a.slow = c->d_slow;
+  a.tt = c->d_tt;
+  a.nsrc = c->nsrc;
+  a.src_xyz = c->d_src;
+  a.st = c->d_state;
+  a.worklist = c->d_worklist;
+  a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
+  a.dirty = c->d_dirty;
+  a.tile_pulls = c->d_tile_pulls;
+  a.ncols = (int)c->star.columns.size();
+  a.nextra = (int)c->star.extra.size();
+  return a;
+}
+
+static int ready(sweeptt_ctx* c) {
+  if (!c) return fail("null context");
+  if (!c->have_model || !c->have_star || !c->have_sources) return fail("context needs a model, a star and start points first");
+  CK(cudaSetDevice(c->device));
+  if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
+    if (!build_maps(c)) return 0;
+    if (!upload_constants(c)) return 0;
+  }
+  return 1;
+}
+
+extern "C" int sweeptt_reset(sweeptt_ctx* c) {
+  if (!ready(c)) return 0;
+  CK(launch_reset(make_args(c), c->opts.max_rounds, c->stream));
+  return 1;
+}
+
+static int enqueue_round(sweeptt_ctx* c, const RelaxArgs& a, unsigned long long cond) {
+  if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
+    CK(launch_relax_tiled(c->tl, c->tm_slow, c->tm_tt, a, c->stream));
+    CK(launch_compact(a, cond, c->stream));
+  } else {
+    CK(launch_relax_simple(a, c->d_star, c->nstar, (unsigned long long)c->pulls_per_round * c->nsrc, c->stream));
+    CK(launch_advance_simple(c->d_state, cond, c->stream));
+  }
+  return 1;
+}
+
+static int read_state(sweeptt_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+// CUDA graph: WHILE(cond) { relax; compact -> sets cond }  -- the whole convergence loop is
+// one graph launch; the host is not consulted between rounds.
+static int build_graph(sweeptt_ctx* c) {
+  if (c->graph_valid) return 1;
+  invalidate_graph(c);
+  cudaGraph_t graph = nullptr;
+  CK(cudaGraphCreate(&graph, 0));
+  cudaGraphConditionalHandle handle;
+  cudaError_t e = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail("cudaGraphConditionalHandleCreate: %s", cudaGetErrorString(e)); }
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  e = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail("cudaGraphAddNode(conditional): %s", cudaGetErrorString(e)); }
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  e = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail("cudaStreamBeginCaptureToGraph: %s", cudaGetErrorString(e)); }
+  const RelaxArgs a = make_args(c);
+  int ok = enqueue_round(c, a, (unsigned long long)handle);
+  cudaGraph_t dummy = nullptr;
+  e = cudaStreamEndCapture(c->stream, &dummy);
+  if (!ok || e != cudaSuccess) { cudaGraphDestroy(graph); return ok ? fail("cudaStreamEndCapture: %s", cudaGetErrorString(e)) : 0; }
+  e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { c->graph_exec = nullptr; return fail("cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  c->graph_valid = true;
+  return 1;
+}
+
+static void fill_stats(sweeptt_ctx* c, sweeptt_stats* st, int rounds_before, long long launches, long long relax_launches,
+                       double relax_ms) {
+  if (!st) return;
+  const SolveState& h = *c->h_state;
+  st->struct_size = sizeof(sweeptt_stats);
+  st->rounds = h.round - rounds_before;
+  st->kernel_used = c->kernel_used;
+  st->devices_used = 1;
+  st->kernel_launches = launches;
+  st->relax_launches = relax_launches;
+  st->tile_visits = (long long)h.tile_visits;
+  st->relaxations = (long long)h.pulls;
+  st->relax_kernel_ms = relax_ms;
+}
+
+static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int* changed_out, sweeptt_stats* stats) {
+  const RelaxArgs a = make_args(c);
+  int loop = c->opts.loop;
+  if (const char* env = getenv("SWEEPTT_LOOP")) {
+    if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
+    if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
+  }
+  if (loop == SWEEPTT_LOOP_AUTO) loop = SWEEPTT_LOOP_GRAPH;
+  const bool profile = c->opts.profile_kernels != 0;
+  if (profile || !to_convergence) loop = SWEEPTT_LOOP_BATCHED;
+  if (!read_state(c)) return 0;
+  const int rounds_before = c->h_state->round;
+  long long launches = 0, relax_launches = 0;
+  double relax_ms = 0;
+
+  if (loop == SWEEPTT_LOOP_GRAPH) {
+    if (!build_graph(c)) {
+      if (c->opts.loop == SWEEPTT_LOOP_GRAPH) return 0;
+      loop = SWEEPTT_LOOP_BATCHED;  // AUTO: fall back to polling
+    }
+  }
+  if (loop == SWEEPTT_LOOP_GRAPH) {
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    if (!read_state(c)) return 0;
+    const int r = c->h_state->round - rounds_before;
+    launches = 2LL * r; relax_launches = r;
+  } else {
+    const int per_poll = to_convergence ? (c->opts.rounds_per_poll > 0 ? c->opts.rounds_per_poll : 8) : fixed_rounds;
+    size_t ev_used = 0;
+    for (;;) {
+      for (int k = 0; k < per_poll; ++k) {
+        if (profile) {
+          if (c->prof_events.size() < ev_used + 2) {
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+            c->prof_events.push_back(e0); c->prof_events.push_back(e1);
+          }
+          CK(cudaEventRecord(c->prof_events[ev_used], c->stream));
+        }
+        if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
+          CK(launch_relax_tiled(c->tl, c->tm_slow, c->tm_tt, a, c->stream));
+        } else {
+          CK(launch_relax_simple(a, c->d_star, c->nstar, (unsigned long long)c->pulls_per_round * c->nsrc, c->stream));
+        }
+        if (profile) { CK(cudaEventRecord(c->prof_events[ev_used + 1], c->stream)); ev_used += 2; }
+        if (c->kernel_used == SWEEPTT_KERNEL_TILED) { CK(launch_compact(a, 0, c->stream)); }
+        else { CK(launch_advance_simple(c->d_state, 0, c->stream)); }
+        launches += 2; relax_launches += 1;
+      }
+      if (!read_state(c)) return 0;
+      if (profile) {
+        for (size_t i = 0; i < ev_used; i += 2) {
+          float ms = 0;
+          CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+          relax_ms += ms;
+        }
+        ev_used = 0;
+      }
+      if (!to_convergence) break;
+      const SolveState& h = *c->h_state;
+      if (h.last_changed_round < h.round) break;  // the last round changed nothing
+      if (c->opts.max_rounds > 0 && h.round - rounds_before >= c->opts.max_rounds) break;
+      if (c->opts.verbose > 0)
+        fprintf(stderr, "[sweeptt] round %d: %u tiles queued, %llu pulls so far\n", h.round, h.count[h.parity], h.pulls);
+    }
+  }
+  if (changed_out) *changed_out = c->h_state->last_changed_round == c->h_state->round;
+  fill_stats(c, stats, rounds_before, launches, relax_launches, relax_ms);
+  return 1;
+}
+
+extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
+  if (!ready(c)) return 0;
+  if (stats) { std::memset(stats, 0, sizeof *stats); }
+  CK(cudaEventRecord(c->ev0, c->stream));
+  CK(launch_reset(make_args(c), c->opts.max_rounds, c->stream));
+  int changed = 0;
+  if (!run_rounds(c, true, 0, &changed, stats)) return 0;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (stats) { stats->solve_ms = ms; stats->kernel_launches += 4; }
+  if (changed && c->opts.max_rounds > 0) return fail("not converged after max_rounds = %d rounds", c->opts.max_rounds);
+  return 1;
+}
+
+extern "C" int sweeptt_step(sweeptt_ctx* c, int rounds, int* changed, sweeptt_stats* stats) {
+  if (!ready(c)) return 0;
+  if (rounds < 1) return fail("sweeptt_step: rounds must be >= 1");
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  CK(cudaEventRecord(c->ev0, c->stream));
+  if (!run_rounds(c, false, rounds, changed, stats)) return 0;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (stats) stats->solve_ms = ms;
+  return 1;
+}
+
+extern "C" int sweeptt_get_tt(sweeptt_ctx* c, int s, float* out) {
+  if (!c || !out) return fail("sweeptt_get_tt: null argument");
+  if (!c->have_sources || s < 0 || s >= c->nsrc) return fail("sweeptt_get_tt: source %d out of range", s);
+  CK(cudaSetDevice(c->device));
+  const size_t dense = (size_t)c->g.nx * c->g.ny * c->g.nz;
+  if (!ensure_stage(c, dense)) return 0;
+  CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, c->d_stage, c->g, c->stream));
+  CK(cudaMemcpyAsync(out, c->d_stage, dense * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+extern "C" int sweeptt_put_tt(sweeptt_ctx* c, int s, const float* in) {
+  if (!c || !in) return fail("sweeptt_put_tt: null argument");
+  if (!ready(c)) return 0;
+  if (s < 0 || s >= c->nsrc) return fail("sweeptt_put_tt: source %d out of range", s);
+  const size_t dense = (size_t)c->g.nx * c->g.ny * c->g.nz;
+  if (!ensure_stage(c, dense)) return 0;
+  CK(cudaMemcpyAsync(c->d_stage, in, dense * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(launch_pad_box(c->d_stage, c->d_tt + (size_t)s * c->g.vol, c->g, c->stream));
+  // every tile of this source must be looked at again
+  // (the pending work list is replaced, so mark every source's tiles, not only this one's)
+  const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
+  CK(cudaMemsetAsync(c->d_dirty, 1, ntiles * c->nsrc, c->stream));
+  CK(launch_compact(make_args(c), 0, c->stream));  // folds the marks into the next work list
+  CK(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+extern "C" int sweeptt_count_violations(sweeptt_ctx* c, int s, long long* violations) {
+  if (!ready(c)) return 0;
+  if (s < 0 || s >= c->nsrc || !violations) return fail("sweeptt_count_violations: bad argument");
+  CK(cudaMemsetAsync(c->d_viol, 0, 8, c->stream));
+  CK(launch_count_violations(make_args(c), s, c->d_star, c->nstar, c->d_viol, c->stream));
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, c->d_viol, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *violations = (long long)v;
+  return 1;
+}
+
+extern "C" long long sweeptt_relaxations_per_round(sweeptt_ctx* c) { return c ? c->pulls_per_round : 0; }
+extern "C" size_t sweeptt_pool_bytes(sweeptt_ctx* c) { return c ? c->pool_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------
+// one-shot solve + multi-start dispatcher
+// ---------------------------------------------------------------------------------------
+static std::mutex g_cache_mu;
+static std::map<int, sweeptt_ctx*> g_cache;
+
+extern "C" void sweeptt_release_cache(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& kv : g_cache) sweeptt_destroy(kv.second);
+  g_cache.clear();
+}
+
+static sweeptt_ctx* cached_ctx(int device, const sweeptt_opts& o) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto it = g_cache.find(device);
+  if (it != g_cache.end()) {
+    sweeptt_ctx* c = it->second;
+    const bool star_opts_changed = c->opts.star_used != o.star_used || c->opts.kernel != o.kernel;
+    c->opts = o;
+    c->opts.device = device;
+    if (star_opts_changed) c->have_star = false;
+    return c;
+  }
+  sweeptt_opts oo = o;
+  oo.device = device;
+  sweeptt_ctx* c = sweeptt_create(&oo);
+  if (c) g_cache[device] = c;
+  return c;
+}
+
+static int solve_on_device(int device, const sweeptt_opts& o, const float* slowness, int nx, int ny, int nz,
+                           const FS* fs, int starsize, const START* starts, int numstart, float* const* tt_out,
+                           sweeptt_stats* st) {
+  sweeptt_ctx* c = cached_ctx(device, o);
+  if (!c) return 0;
+  std::memset(st, 0, sizeof *st);
+  CK(cudaSetDevice(device));
+  CK(cudaEventRecord(c->ev2, c->stream));
+  if (!sweeptt_set_model(c, slowness, nx, ny, nz)) return 0;
+  CK(cudaEventRecord(c->ev3, c->stream));
+  const bool same_star = c->have_star && (int)c->fs.size() == starsize &&
+                         std::memcmp(c->fs.data(), fs, sizeof(FS) * starsize) == 0;
+  if (!same_star && !sweeptt_set_star(c, fs, starsize)) return 0;
+  if (!sweeptt_set_sources(c, starts, numstart)) return 0;
+  if (!sweeptt_run(c, st)) return 0;
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+  st->h2d_ms = ms;
+  st->h2d_bytes = (long long)nx * ny * nz * 4;
+  CK(cudaEventRecord(c->ev2, c->stream));
+  // device -> host: un-pad into the dense staging box, then one contiguous copy per source
+  const size_t dense = (size_t)nx * ny * nz;
+  for (int s = 0; s < numstart; ++s) {
+    CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, c->d_stage, c->g, c->stream));
+    CK(cudaMemcpyAsync(tt_out[s], c->d_stage, dense * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaEventRecord(c->ev3, c->stream));
+  CK(cudaEventSynchronize(c->ev3));
+  CK(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+  st->d2h_ms = ms;
+  st->d2h_bytes = (long long)dense * 4 * numstart;
+  st->kernel_launches += 2 + numstart;
+  return 1;
+}
+
+extern "C" int sweeptt_solve(const float* slowness, int nx, int ny, int nz, const struct FS* fs, int starsize,
+                             const struct START* starts, int numstart, float* const* tt_out, const sweeptt_opts* opts,
+                             sweeptt_stats* stats) {
+  if (!slowness || !fs || !starts || !tt_out) return fail("sweeptt_solve: null argument");
+  if (numstart <= 0) return fail("sweeptt_solve: need at least one start point");
+  sweeptt_opts o{};
+  if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof o, opts->struct_size > 0 ? opts->struct_size : sizeof o));
+  const int ndev_avail = sweeptt_device_count();
+  if (ndev_avail <= 0) return fail("no CUDA device available: the sweep has no CPU fallback");
+  int ndev = std::max(1, o.num_devices);
+  if (ndev > ndev_avail) return fail("num_devices = %d but only %d CUDA devices are visible", ndev, ndev_avail);
+  ndev = std::min(ndev, numstart);
+  sweeptt_stats total{};
+  total.struct_size = sizeof total;
+  if (ndev == 1) {
+    int dev = o.device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (!solve_on_device(dev, o, slowness, nx, ny, nz, fs, starsize, starts, numstart, tt_out, &total)) return 0;
+  } else {
+    // Sources are independent (mpi/backup.c:351-363): deal them round-robin, one host thread
+    // and one stream per GPU, no inter-GPU traffic.
+    std::vector<std::vector<START>> shard(ndev);
+    std::vector<std::vector<float*>> outs(ndev);
+    for (int s = 0; s < numstart; ++s) {
+      shard[s % ndev].push_back(starts[s]);
+      outs[s % ndev].push_back(tt_out[s]);
+    }
+    std::vector<sweeptt_stats> st(ndev);
+    std::vector<int> ok(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d)
+      th.emplace_back([&, d] {
+        ok[d] = solve_on_device(d, o, slowness, nx, ny, nz, fs, starsize, shard[d].data(), (int)shard[d].size(),
+                                outs[d].data(), &st[d]);
+        if (!ok[d]) errs[d] = g_err;
+      });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < ndev; ++d)
+      if (!ok[d]) return fail("device %d: %s", d, errs[d].c_str());
+    for (int d = 0; d < ndev; ++d) {
+      total.rounds = std::max(total.rounds, st[d].rounds);
+      total.kernel_used = st[d].kernel_used;
+      total.kernel_launches += st[d].kernel_launches;
+      total.relax_launches += st[d].relax_launches;
+      total.tile_visits += st[d].tile_visits;
+      total.relaxations += st[d].relaxations;
+      total.solve_ms = std::max(total.solve_ms, st[d].solve_ms);
+      total.relax_kernel_ms = std::max(total.relax_kernel_ms, st[d].relax_kernel_ms);
+      total.h2d_ms = std::max(total.h2d_ms, st[d].h2d_ms);
+      total.d2h_ms = std::max(total.d2h_ms, st[d].d2h_ms);
+      total.h2d_bytes += st[d].h2d_bytes;
+      total.d2h_bytes += st[d].d2h_bytes;
+    }
+  }
+  total.devices_used = ndev;
+  if (stats) *stats = total;
+  return 1;
+}
+
+extern "C" int sweeptt_solve_slabs(const float*, int, int, int, const struct FS*, int, struct START, float*,
+                                   const sweeptt_opts*, sweeptt_stats*) {
+  return fail("sweeptt_solve_slabs: slab decomposition is not built yet (SURVEY.md §8e, config 5)");
+}
