@@ -64,8 +64,9 @@ struct StarDev {   // star as the simple kernel / verifier read it (global memor
   int guarded;
 };
 
-constexpr int MAX_COLUMNS = 256;
+constexpr int MAX_COLUMNS = 320;
+constexpr int MAX_PATTERNS = 31;
 constexpr int MAX_COL_HD = 4096;
-constexpr int MAX_EXTRA = 64;
+constexpr int MAX_EXTRA = 512;
 
 }  // namespace sweeptt

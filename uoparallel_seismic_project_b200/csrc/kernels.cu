@@ -112,18 +112,128 @@ struct TileDims {
   static constexpr int SXD = TX + 2 * RXY;
   static constexpr int SYD = TY + 2 * RXY;
   static constexpr int BOX_FLOATS = SXD * SYD * SZD;
-  static constexpr size_t SMEM = 2 * sizeof(float) * BOX_FLOATS + 1024;  // + alignment slack
+  // second box starts on a 1024-byte boundary (TMA destinations must be 128-byte aligned)
+  static constexpr int BOX_STRIDE = (BOX_FLOATS * 4 + 1023) / 1024 * 1024 / 4;
+  static constexpr size_t SMEM = sizeof(float) * (BOX_STRIDE + BOX_FLOATS) + 1024;  // + alignment slack
 };
 
-template <int RXY>
+// ---- column phase -------------------------------------------------------------------------
+// One (i,j) column of the star = one 24-float register window of slowness and of travel time
+// (LDS.128 granules) + the column's k offsets run out of registers.
+template <uint32_t... M>
+struct MaskList {};  // compile-time k-pattern list of a stock star; empty = generic kernel
+
+__host__ __device__ constexpr uint32_t granules_of(uint32_t kmask) {
+  uint32_t g = 0;
+  for (int b = 0; b <= 2 * ZHALO; ++b)
+    if (kmask & (1u << b))
+      for (int k = 0; k < KZ; ++k) g |= 1u << ((k + b) / 4);
+  return g;
+}
+
+template <uint32_t GM>
+__device__ __forceinline__ void load_window(const float* __restrict__ pv, const float* __restrict__ pt,
+                                            float (&W)[WIN], float (&T)[WIN]) {
+#pragma unroll
+  for (int g = 0; g < WIN / 4; ++g) {
+    if (GM & (1u << g)) {
+      const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * g);
+      const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * g);
+      W[4 * g] = wv.x; W[4 * g + 1] = wv.y; W[4 * g + 2] = wv.z; W[4 * g + 3] = wv.w;
+      T[4 * g] = wt.x; T[4 * g + 1] = wt.y; T[4 * g + 2] = wt.z; T[4 * g + 3] = wt.w;
+    }
+  }
+}
+
+// the arithmetic contract, once: fl(fl(hd * fl(v_n + v_m)) + tt_m), min-reduced
+template <uint32_t KMASK>
+__device__ __forceinline__ void relax_column(const float (&W)[WIN], const float (&T)[WIN], int hi,
+                                             const float (&vn)[KZ], float (&acc)[KZ]) {
+#pragma unroll
+  for (int b = 0; b <= 2 * ZHALO; ++b) {  // k = b - ZHALO
+    if (KMASK & (1u << b)) {
+      const float hd = c_col_hd[hi++];
+#pragma unroll
+      for (int k = 0; k < KZ; ++k) {
+        const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
+        acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
+      }
+    }
+  }
+}
+
+// all columns [cbeg,cend) share the compile-time pattern KMASK: branch-free unrolled blocks,
+// the next column's window is fetched (ping-pong registers) while the current one computes
+template <uint32_t KMASK>
+__device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const float* __restrict__ st, int b0,
+                                            int cbeg, int cend, const float (&vn)[KZ], float (&acc)[KZ]) {
+  constexpr uint32_t GM = granules_of(KMASK);
+  // the host pads every pattern group to an EVEN number of columns (a duplicated column is
+  // harmless: min is idempotent), so the ping-pong loop needs no tail copy of the code
+  if (cbeg >= cend) return;
+  float Wa[WIN], Ta[WIN], Wb[WIN], Tb[WIN];
+  ColumnDev ca = c_cols[cbeg];
+  load_window<GM>(sv + b0 + ca.soff, st + b0 + ca.soff, Wa, Ta);
+  for (int c = cbeg; c < cend; c += 2) {
+    const ColumnDev cb = c_cols[c + 1];
+    load_window<GM>(sv + b0 + cb.soff, st + b0 + cb.soff, Wb, Tb);
+    relax_column<KMASK>(Wa, Ta, ca.hd_begin, vn, acc);
+    ca = c_cols[(c + 2 < cend) ? c + 2 : c];
+    load_window<GM>(sv + b0 + ca.soff, st + b0 + ca.soff, Wa, Ta);
+    relax_column<KMASK>(Wb, Tb, cb.hd_begin, vn, acc);
+  }
+}
+
+template <uint32_t... M>
+__device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
+                                              const float* __restrict__ st, int b0, const RelaxArgs& a,
+                                              const float (&vn)[KZ], float (&acc)[KZ]) {
+  if constexpr (sizeof...(M) == 0) {
+    // generic: runtime masks (any star that fits the halo)
+    float W[WIN], T[WIN];  // granules a column does not touch keep stale, never-read values
+#pragma unroll
+    for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
+    for (int c = 0; c < a.ncols; ++c) {
+      const ColumnDev col = c_cols[c];
+      const float* pv = sv + b0 + col.soff;
+      const float* pt = st + b0 + col.soff;
+#pragma unroll
+      for (int g = 0; g < WIN / 4; ++g) {
+        if (col.gmask & (1u << g)) {
+          const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * g);
+          const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * g);
+          W[4 * g] = wv.x; W[4 * g + 1] = wv.y; W[4 * g + 2] = wv.z; W[4 * g + 3] = wv.w;
+          T[4 * g] = wt.x; T[4 * g + 1] = wt.y; T[4 * g + 2] = wt.z; T[4 * g + 3] = wt.w;
+        }
+      }
+      int hi = col.hd_begin;
+#pragma unroll
+      for (int b = 0; b <= 2 * ZHALO; ++b) {
+        if (col.kmask & (1u << b)) {
+          const float hd = c_col_hd[hi++];
+#pragma unroll
+          for (int k = 0; k < KZ; ++k) {
+            const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
+            acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
+          }
+        }
+      }
+    }
+  } else {
+    int p = 0;
+    ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, acc), ++p), ...);
+  }
+}
+
+template <int RXY, typename STAR>
 __global__ void __launch_bounds__(TILE_THREADS, (RXY == 7) ? 1 : 2)
 relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
-            const RelaxArgs a) {
+            const __grid_constant__ RelaxArgs a) {
   using D = TileDims<RXY>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned carve-up: [slowness box][travel-time box]
   float* sv = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  float* st = sv + D::BOX_FLOATS;
+  float* st = sv + D::BOX_STRIDE;
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_tile;
 
@@ -192,37 +302,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < KZ; ++k) acc[k] = told[k];
 
-      // ---- main loop: one (i,j) column of the star per iteration ----
-      float W[WIN], T[WIN];  // register windows; granules a column does not touch keep stale
-                             // (finite-or-INF, never read) values from earlier columns
-#pragma unroll
-      for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
-      for (int c = 0; c < a.ncols; ++c) {
-        const ColumnDev col = c_cols[c];
-        const float* pv = sv + b0 + col.soff;
-        const float* pt = st + b0 + col.soff;
-#pragma unroll
-        for (int g = 0; g < WIN / 4; ++g) {
-          if (col.gmask & (1u << g)) {
-            const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * g);
-            const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * g);
-            W[4 * g] = wv.x; W[4 * g + 1] = wv.y; W[4 * g + 2] = wv.z; W[4 * g + 3] = wv.w;
-            T[4 * g] = wt.x; T[4 * g + 1] = wt.y; T[4 * g + 2] = wt.z; T[4 * g + 3] = wt.w;
-          }
-        }
-        int hi = col.hd_begin;
-#pragma unroll
-        for (int b = 0; b <= 2 * ZHALO; ++b) {  // k = b - ZHALO
-          if (col.kmask & (1u << b)) {
-            const float hd = c_col_hd[hi++];
-#pragma unroll
-            for (int k = 0; k < KZ; ++k) {
-              const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
-              acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
-            }
-          }
-        }
-      }
+      columns_phase(STAR{}, sv, st, b0, a, vn, acc);
 
       // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
       //      serial_new/...c:219-221 with :160) and duplicates ----
@@ -461,13 +541,36 @@ void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd) {
   *sxd = TX + 2 * rxy; *syd = TY + 2 * rxy; *szd = SZD;
 }
 
-template <int RXY>
+// stock stars: pattern lists generated from the reference's shipped star files
+#define SWEEPTT_STOCK_STAR(id, name, rxy, ...) using Star_##name = MaskList<__VA_ARGS__>;
+#include "stock_stars.inc"
+#undef SWEEPTT_STOCK_STAR
+using StarGeneric = MaskList<>;
+
+template <uint32_t... M>
+static int masks_match(MaskList<M...>, const uint32_t* masks, int n) {
+  constexpr uint32_t want[] = {M..., 0u};
+  if (n != (int)sizeof...(M)) return 0;
+  for (int i = 0; i < n; ++i)
+    if (masks[i] != want[i]) return 0;
+  return 1;
+}
+
+int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed) {
+#define SWEEPTT_STOCK_STAR(id, name, rxy, ...) \
+  if (rxy_needed == rxy && masks_match(Star_##name{}, masks_ascending, n)) return id;
+#include "stock_stars.inc"
+#undef SWEEPTT_STOCK_STAR
+  return 0;
+}
+
+template <int RXY, typename STAR>
 static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   using D = TileDims<RXY>;
-  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
   if (e != cudaSuccess) return e;
   int per_sm = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY>, TILE_THREADS, D::SMEM);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR>, TILE_THREADS, D::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return e;
@@ -477,21 +580,33 @@ static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   out->smem_bytes = D::SMEM;
   return cudaSuccess;
 }
-cudaError_t tiled_prepare(int rxy, int device, TiledLaunch* out) {
+cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
+  out->stock_id = stock_id;
+#define SWEEPTT_STOCK_STAR(id, name, r, ...) \
+  if (stock_id == id) return prepare_variant<r, Star_##name>(device, out);
+#include "stock_stars.inc"
+#undef SWEEPTT_STOCK_STAR
   switch (rxy) {
-    case 2: return prepare_variant<2>(device, out);
-    case 4: return prepare_variant<4>(device, out);
-    case 7: return prepare_variant<7>(device, out);
+    case 2: return prepare_variant<2, StarGeneric>(device, out);
+    case 4: return prepare_variant<4, StarGeneric>(device, out);
+    case 7: return prepare_variant<7, StarGeneric>(device, out);
   }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
                                const RelaxArgs& a, cudaStream_t stream) {
+#define SWEEPTT_STOCK_STAR(id, name, r, ...)                                                                  \
+  if (tl.stock_id == id) {                                                                                    \
+    relax_tiled<r, Star_##name><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);         \
+    return cudaGetLastError();                                                                                \
+  }
+#include "stock_stars.inc"
+#undef SWEEPTT_STOCK_STAR
   switch (tl.rxy) {
-    case 2: relax_tiled<2><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
-    case 4: relax_tiled<4><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
-    case 7: relax_tiled<7><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 2: relax_tiled<2, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 4: relax_tiled<4, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 7: relax_tiled<7, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

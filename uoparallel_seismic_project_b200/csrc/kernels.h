@@ -9,6 +9,7 @@ namespace sweeptt {
 
 struct TiledLaunch {
   int rxy;                   // halo template: 2, 4 or 7
+  int stock_id;              // 0 = generic runtime-mask kernel, else a stock-star instantiation
   int grid;                  // persistent CTAs
   size_t smem_bytes;
 };
@@ -18,7 +19,9 @@ int tiled_variant_for_radius(int r);
 // smem row/plane pitches of a variant (host needs them to precompute column offsets).
 void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd);
 // Occupancy-derived persistent grid + opt-in shared memory; returns cudaSuccess or an error.
-cudaError_t tiled_prepare(int rxy, int device, TiledLaunch* out);
+cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out);
+// Stock-star instantiation whose compile-time pattern list equals `masks` (ascending), or 0.
+int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed);
 
 // Upload the column tables into __constant__ memory (stream ordered).
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
@@ -36,6 +39,7 @@ struct RelaxArgs {
   unsigned char* dirty;        // nsrc * ntiles flags (marks for the next round)
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
+  int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow,

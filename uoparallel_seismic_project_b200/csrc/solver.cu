@@ -155,6 +155,8 @@ struct sweeptt_ctx {
   CUtensorMap tm_slow{}, tm_tt{};
   bool maps_valid = false;
   int consts_rxy = -1;  // variant the __constant__ tables were built for
+  std::vector<int> pat_begin;  // column ranges per k-pattern (stock-star kernels)
+  std::vector<PullColumn> dev_columns;  // pattern-sorted, even-padded columns as uploaded
 
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
@@ -386,7 +388,7 @@ extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsiz
 static int choose_kernel(sweeptt_ctx* c) {
   const int want = c->opts.kernel;
   int rxy = 0;
-  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() <= MAX_COLUMNS &&
+  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() + MAX_PATTERNS <= MAX_COLUMNS + 0 &&
                     (int)c->star.col_hd.size() <= MAX_COL_HD && (int)c->star.extra.size() <= MAX_EXTRA;
   if (fits) rxy = tiled_variant_for_radius(std::max(c->star.rx, c->star.ry));
   if (want == SWEEPTT_KERNEL_SIMPLE || (want == SWEEPTT_KERNEL_AUTO && rxy == 0)) {
@@ -396,11 +398,38 @@ static int choose_kernel(sweeptt_ctx* c) {
   if (rxy == 0)
     return fail("the tiled kernel holds |i|,|j| <= %d, |k| <= %d and <= %d guarded offsets; this star needs (%d,%d,%d) / %d",
                 RXY_MAX, KHALO, MAX_EXTRA, c->star.rx, c->star.ry, c->star.rz, (int)c->star.extra.size());
+  // group the columns by k-pattern (ascending mask): the stock-star kernels run one unrolled
+  // code block per pattern over a contiguous column range
+  std::stable_sort(c->star.columns.begin(), c->star.columns.end(),
+                   [](const PullColumn& a, const PullColumn& b) { return a.kmask < b.kmask; });
+  std::vector<uint32_t> masks;
+  c->pat_begin.clear();
+  {
+    // pad every pattern group to an even column count by repeating its last column (relaxing a
+    // column twice is harmless) -- the stock-star kernels process columns in ping-pong pairs
+    std::vector<PullColumn> padded;
+    size_t i = 0;
+    while (i < c->star.columns.size()) {
+      size_t j = i;
+      while (j < c->star.columns.size() && c->star.columns[j].kmask == c->star.columns[i].kmask) ++j;
+      masks.push_back(c->star.columns[i].kmask);
+      c->pat_begin.push_back((int)padded.size());
+      padded.insert(padded.end(), c->star.columns.begin() + i, c->star.columns.begin() + j);
+      if ((j - i) & 1) padded.push_back(c->star.columns[j - 1]);
+      i = j;
+    }
+    c->pat_begin.push_back((int)padded.size());
+    c->dev_columns = padded;
+  }
+  int stock = 0;
+  if ((int)masks.size() <= MAX_PATTERNS && !getenv("SWEEPTT_GENERIC"))
+    stock = tiled_stock_star_for(masks.data(), (int)masks.size(), rxy);
   const char* force = getenv("SWEEPTT_FORCE_RXY");  // testing: run a small star in a wider halo variant
-  if (force && atoi(force) >= rxy) rxy = tiled_variant_for_radius(atoi(force));
-  CK(tiled_prepare(rxy, c->device, &c->tl));
+  if (force && atoi(force) >= rxy) { rxy = tiled_variant_for_radius(atoi(force)); stock = 0; }
+  CK(tiled_prepare(rxy, stock, c->device, &c->tl));
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
+  c->consts_rxy = -1;
   return 1;
 }
 
@@ -410,9 +439,9 @@ static int upload_constants(sweeptt_ctx* c) {
   if (it != g_const_owner.end() && it->second == c && c->consts_rxy == c->tl.rxy) return 1;
   int sxd, syd, szd;
   tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
-  std::vector<ColumnDev> cols(c->star.columns.size());
+  std::vector<ColumnDev> cols(c->dev_columns.size());
   for (size_t i = 0; i < cols.size(); ++i) {
-    const PullColumn& pc = c->star.columns[i];
+    const PullColumn& pc = c->dev_columns[i];
     ColumnDev d;
     d.soff = pc.i * syd * szd + pc.j * szd;
     d.kmask = pc.kmask;
@@ -531,8 +560,9 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
   a.dirty = c->d_dirty;
   a.tile_pulls = c->d_tile_pulls;
-  a.ncols = (int)c->star.columns.size();
+  a.ncols = (int)c->dev_columns.size();
   a.nextra = (int)c->star.extra.size();
+  for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   return a;
 }
 
