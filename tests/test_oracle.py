@@ -40,7 +40,8 @@ def test_star_distances_match_reference():
     lib = oracle.reference()
     for name in ("3", "5", "818"):
         off = np.ascontiguousarray(W.star(name), np.int32)
-        assert lib.refh_set_star(off.ctypes.data, len(off))
+        import ctypes
+        assert lib.refh_set_star(ctypes.c_void_p(off.ctypes.data), len(off))
         d_ref = np.array([lib.refh_star_distance(l) for l in range(len(off))], np.float32)
         assert_bit_equal(oracle.star_distances(off), d_ref)
 
