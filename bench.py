@@ -207,7 +207,8 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # ---- device-resident leg: slowness + star + sources already in HBM -------------------------
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # not the legacy default stream: the solver captures a CUDA graph on it
+    torch.cuda.set_stream(stream)
     ctx = P.SweepContext(device=local)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_model(v); ctx.set_star(star); ctx.set_sources(starts)

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sweeptt.h declares, and its compute
+entry points fail LOUDLY without a CUDA device (no CPU fallback, no oracle behind the product)."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import uoparallel_seismic_project_b200 as P
+from uoparallel_seismic_project_b200 import api, workloads as W
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "sweeptt.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sweeptt_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = P.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sweeptt.h but not exported by libsweeptt.so"
+    assert set(syms) == set(api._EXPORTS)
+
+
+def test_struct_layouts_match_reference():
+    assert ctypes.sizeof(P.FS) == 16 and ctypes.sizeof(P.START) == 12  # serial_new/...c:46-58
+    assert P.load_library().sweeptt_version().decode().startswith("sweeptt")
+
+
+def test_product_does_not_route_through_the_oracle():
+    """Nothing under the package imports, loads or links the test oracle."""
+    for p in (ROOT / "uoparallel_seismic_project_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cpp", ".h", ".inc"}:
+            text = p.read_text()
+            for needle in ("import oracle", "from oracle", "liboracle", "libref_sweep", "oracle/_ref"):
+                assert needle not in text, f"{p} references the oracle ({needle})"
+    ldd = __import__("subprocess").run(["ldd", str(P.lib_path())], capture_output=True, text=True).stdout
+    assert "liboracle" not in ldd and "libref_sweep" not in ldd
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="this check is for the GPU-less build container")
+def test_compute_fails_loudly_without_a_gpu():
+    assert P.device_count() == 0
+    v = W.random_field((4, 4, 4))
+    with pytest.raises(P.SweepError, match="no CUDA device"):
+        P.solve(v, W.star("3"), [(0, 0, 0)])
+    with pytest.raises(P.SweepError, match="no CUDA device"):
+        P.SweepContext()
+
+
+def test_star_distance_helper_matches_reference_formula():
+    fs = P.make_star(W.star("818"))
+    for l in (0, 100, 817):
+        i, j, k = fs[l].i, fs[l].j, fs[l].k
+        want = np.float32(10.0) * np.float32(np.sqrt(np.float64(i * i + j * j + k * k)))
+        assert np.float32(fs[l].d) == want
