@@ -145,20 +145,84 @@ __device__ __forceinline__ void load_window(const float* __restrict__ pv, const 
   }
 }
 
-// the arithmetic contract, once: fl(fl(hd * fl(v_n + v_m)) + tt_m), min-reduced
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2) ---------------------------------------
+// Two IEEE-754 round-to-nearest fp32 operations per instruction: same bits as the scalar ops,
+// half the issue slots.  NEVER an fma: ptxas has been seen to contract mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 (even with --fmad=false), which would break the bit-exactness
+// contract, so the product is produced by fma.rn.f32x2(a, b, -0.0) with a RUNTIME -0.0 operand:
+// a*b + (-0) rounds exactly like a*b (signed zeros included) and an FFMA2 cannot be fused into
+// the following add.  tests/test_sass.py greps the SASS.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 mul2_exact(u64 a, u64 b, u64 negzero2) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(negzero2));
+  return d;
+}
+
+__host__ __device__ constexpr int popc_below(uint32_t m, int b) {
+  int n = 0;
+  for (int i = 0; i < b; ++i) n += (m >> i) & 1u;
+  return n;
+}
+
+// The arithmetic contract, once: cand = fl(fl(hd * fl(v_n + v_m)) + tt_m); acc = min(acc, cand).
+// Node pairs (2j,2j+1) for even window shifts, (2j+1,2j+2) + two scalar ends for odd shifts, so
+// that the window operands are always naturally aligned register pairs.  Candidates of two
+// consecutive offsets are folded with one 3-input min (FMNMX3).
 template <uint32_t KMASK>
 __device__ __forceinline__ void relax_column(const float (&W)[WIN], const float (&T)[WIN], int hi,
-                                             const float (&vn)[KZ], float (&acc)[KZ]) {
+                                             const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                             const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
+  float pend[KZ];
 #pragma unroll
   for (int b = 0; b <= 2 * ZHALO; ++b) {  // k = b - ZHALO
     if (KMASK & (1u << b)) {
       const float hd = c_col_hd[hi++];
+      const u64 hd2 = pack2(hd, hd);
+      float cand[KZ];
+      if ((b & 1) == 0) {
 #pragma unroll
-      for (int k = 0; k < KZ; ++k) {
-        const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
-        acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
+        for (int j = 0; j < KZ / 2; ++j) {
+          const u64 sum = add2(vnE[j], pack2(W[2 * j + b], W[2 * j + b + 1]));
+          const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[2 * j + b], T[2 * j + b + 1]));
+          unpack2(c2, cand[2 * j], cand[2 * j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KZ / 2 - 1; ++j) {
+          const int k = 2 * j + 1;
+          const u64 sum = add2(vnO[j], pack2(W[k + b], W[k + b + 1]));
+          const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[k + b], T[k + b + 1]));
+          unpack2(c2, cand[k], cand[k + 1]);
+        }
+        cand[0] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[0], W[b])), T[b]);
+        cand[KZ - 1] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[KZ - 1], W[KZ - 1 + b])), T[KZ - 1 + b]);
+      }
+      if (popc_below(KMASK, b) & 1) {
+#pragma unroll
+        for (int k = 0; k < KZ; ++k) acc[k] = fminf(fminf(acc[k], pend[k]), cand[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < KZ; ++k) pend[k] = cand[k];
       }
     }
+  }
+  if (popc_below(KMASK, 2 * ZHALO + 1) & 1) {
+#pragma unroll
+    for (int k = 0; k < KZ; ++k) acc[k] = fminf(acc[k], pend[k]);
   }
 }
 
@@ -166,7 +230,8 @@ __device__ __forceinline__ void relax_column(const float (&W)[WIN], const float 
 // the next column's window is fetched (ping-pong registers) while the current one computes
 template <uint32_t KMASK>
 __device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const float* __restrict__ st, int b0,
-                                            int cbeg, int cend, const float (&vn)[KZ], float (&acc)[KZ]) {
+                                            int cbeg, int cend, const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                            const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
   constexpr uint32_t GM = granules_of(KMASK);
   // the host pads every pattern group to an EVEN number of columns (a duplicated column is
   // harmless: min is idempotent), so the ping-pong loop needs no tail copy of the code
@@ -177,10 +242,10 @@ __device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const 
   for (int c = cbeg; c < cend; c += 2) {
     const ColumnDev cb = c_cols[c + 1];
     load_window<GM>(sv + b0 + cb.soff, st + b0 + cb.soff, Wb, Tb);
-    relax_column<KMASK>(Wa, Ta, ca.hd_begin, vn, acc);
+    relax_column<KMASK>(Wa, Ta, ca.hd_begin, vn, vnE, vnO, nz2, acc);
     ca = c_cols[(c + 2 < cend) ? c + 2 : c];
     load_window<GM>(sv + b0 + ca.soff, st + b0 + ca.soff, Wa, Ta);
-    relax_column<KMASK>(Wb, Tb, cb.hd_begin, vn, acc);
+    relax_column<KMASK>(Wb, Tb, cb.hd_begin, vn, vnE, vnO, nz2, acc);
   }
 }
 
@@ -220,8 +285,14 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
       }
     }
   } else {
+    u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
+#pragma unroll
+    for (int j = 0; j < KZ / 2; ++j) vnE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < KZ / 2 - 1; ++j) vnO[j] = pack2(vn[2 * j + 1], vn[2 * j + 2]);
+    const u64 nz2 = pack2(a.neg_zero, a.neg_zero);
     int p = 0;
-    ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, acc), ++p), ...);
+    ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, vnE, vnO, nz2, acc), ++p), ...);
   }
 }
 

@@ -39,6 +39,7 @@ struct RelaxArgs {
   unsigned char* dirty;        // nsrc * ntiles flags (marks for the next round)
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
+  float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
 

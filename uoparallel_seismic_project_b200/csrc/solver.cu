@@ -562,6 +562,7 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.tile_pulls = c->d_tile_pulls;
   a.ncols = (int)c->dev_columns.size();
   a.nextra = (int)c->star.extra.size();
+  a.neg_zero = -0.0f;
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   return a;
 }
