@@ -87,6 +87,8 @@ typedef struct sweeptt_stats {
   long long relax_launches;  /* launches of the relaxation kernel                          */
   double h2d_ms, d2h_ms;     /* host<->device copies performed by the call                 */
   long long h2d_bytes, d2h_bytes;
+  long long units_run;       /* (warp, tile) work units executed by the tiled kernel          */
+  long long units_changed;   /* ... of which lowered at least one travel time                 */
 } sweeptt_stats;
 
 /* ---- discovery / errors ------------------------------------------------- */

@@ -51,6 +51,21 @@ def test_small_star_in_wider_halo_variants(rxy, golden_small, monkeypatch):
         assert_bit_equal(ctx.get_tt(0), m["tt"])
 
 
+@pytest.mark.parametrize("axis", ["0", "1", "2"])
+def test_every_window_axis_permutation(axis, golden_small, monkeypatch):
+    """The solver permutes axes so the register-window axis tiles best; force each choice."""
+    monkeypatch.setenv("SWEEPTT_WINDOW_AXIS", axis)
+    for m in golden_small:
+        if m["idx"] != 0:
+            continue
+        v = make_field(m["kind"], m["dims"], m["seed"])
+        with P.SweepContext(kernel=api.KERNEL_TILED) as ctx:
+            ctx.set_model(v); ctx.set_star(W.star(m["star"])); ctx.set_sources([m["start"]])
+            ctx.run()
+            assert ctx.count_violations(0) == 0
+            assert_bit_equal(ctx.get_tt(0), m["tt"], f"{m['case']} window axis {axis}")
+
+
 @pytest.mark.parametrize("dims", [(1, 1, 1), (1, 9, 1), (8, 8, 32), (9, 9, 33), (7, 7, 31), (16, 8, 64), (3, 40, 5)])
 def test_degenerate_and_tile_edge_shapes(dims):
     v = W.random_field(dims, seed=sum(dims))

@@ -39,7 +39,7 @@ def test_relax_kernels_are_tma_and_never_fuse_multiply_add():
                 # addend must be the broadcast scalar -0.0 (".F32"), never a packed travel-time pair (".F32x2")
                 assert re.search(r"FFMA2 R\d+, .*, U?R\d+(\.reuse)?\.F32 ;", l), f"{name}: FFMA2 with a packed addend: {l}"
     stock = [k for k in relax if "MaskListIJLj" in k]
-    assert len(stock) == 3
+    assert len(stock) >= 3
     for name in stock:
         text = "\n".join(relax[name])
         assert "FADD2" in text and "FMNMX3" in text, f"{name}: packed fp32x2 path missing"

@@ -19,6 +19,7 @@ for loop, prof in ((api.LOOP_BATCHED, 1), (api.LOOP_BATCHED, 0), (api.LOOP_GRAPH
         full = ctx.relaxations_per_round * nsrc
         print(f"loop={loop} prof={prof}: rounds={st.rounds} solve={st.solve_ms:.2f}ms relax_kernel={st.relax_kernel_ms:.2f}ms "
               f"GRelax={st.relaxations/1e9:.2f} ({st.relaxations/full:.1f} full rounds) tiles={st.tile_visits} "
-              f"-> {st.relaxations/st.solve_ms/1e6:.1f} GRelax/s, {nsrc/st.solve_ms*1e3:.1f} sources/s", flush=True)
+              f"-> {st.relaxations/st.solve_ms/1e6:.1f} GRelax/s, {nsrc/st.solve_ms*1e3:.1f} sources/s "
+              f"units changed/run = {st.units_changed}/{st.units_run}", flush=True)
         if prof:
             print("   violations:", [ctx.count_violations(s) for s in range(nsrc)])

@@ -49,6 +49,7 @@ class _Stats(C.Structure):
         ("kernel_launches", C.c_longlong), ("tile_visits", C.c_longlong), ("relaxations", C.c_longlong),
         ("solve_ms", C.c_double), ("relax_kernel_ms", C.c_double), ("relax_launches", C.c_longlong),
         ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+        ("units_run", C.c_longlong), ("units_changed", C.c_longlong),
     ]
 
 
@@ -67,6 +68,8 @@ class SweepStats:
     d2h_ms: float = 0.0
     h2d_bytes: int = 0
     d2h_bytes: int = 0
+    units_run: int = 0
+    units_changed: int = 0
 
     @classmethod
     def _from(cls, s: _Stats) -> "SweepStats":

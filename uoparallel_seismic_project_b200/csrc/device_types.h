@@ -21,8 +21,14 @@ constexpr int TILE_THREADS = TX * TY * (TZ / KZ);
 // the inner loop), travel time = +INF.
 constexpr int AX = 7, AY = 7, AZ = ZHALO;
 
+// The kernels work in a PERMUTED coordinate system: kernel axis q is the caller's axis perm[q],
+// chosen so that the register-window axis (kernel z, tiled by 32) is the caller axis that tiles
+// best (241x241x51: windows run along the caller's y, 51 is tiled by 8).  The permutation lives
+// only in the pad/un-pad kernels, the star offsets and the start points.
 struct BoxGeom {
-  int nx, ny, nz;      // logical dims
+  int nx, ny, nz;      // logical dims in KERNEL axis order
+  int perm[3];         // kernel axis q = caller axis perm[q]
+  long long dstride[3];// stride (floats) of kernel axis q in the caller's dense FLOATBOX
   int px, py, pz;      // padded dims
   int ntx, nty, ntz;   // tiles per axis
   long long sx;        // py*pz
@@ -39,7 +45,10 @@ struct SolveState {
   unsigned ticket;           // last-block-done ticket of the compaction kernel
   unsigned long long tile_visits;
   unsigned long long pulls;  // in-bounds pull evaluations executed
+  unsigned long long units_run;      // (warp, tile) units that ran the column phase
+  unsigned long long units_changed;  // ... of which lowered at least one travel time
   int max_rounds;            // 0 = unlimited; the graph WHILE loop stops here
+  unsigned kmin_bits;        // smallest activation key among dirty tiles (scan pass of the compaction)
   int pad;
 };
 

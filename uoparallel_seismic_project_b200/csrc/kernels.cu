@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <limits>
 
@@ -307,6 +308,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   float* st = sv + D::BOX_STRIDE;
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_tile;
+  __shared__ unsigned s_tmin;   // float bits of the smallest travel time this tile lowered
+  __shared__ unsigned s_zmask;  // which z chunks changed
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -336,6 +339,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     if (tid == 0) {
       const unsigned i = atomicAdd(&S->cursor, 1u);
       s_tile = (i < cnt) ? (int)wl[i] : -1;
+      s_tmin = 0x7f800000u;
+      s_zmask = 0u;
     }
     __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile
     const int tile = s_tile;
@@ -399,22 +404,41 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
           if (gz + k == pz) acc[k] = told[k];
       }
 
+      float tmin = CUDART_INF_F;
 #pragma unroll
-      for (int k = 0; k < KZ; ++k) changed |= (acc[k] < told[k]);
+      for (int k = 0; k < KZ; ++k) {
+        const bool lower = acc[k] < told[k];
+        changed |= lower;
+        tmin = lower ? fminf(tmin, acc[k]) : tmin;
+      }
       if (changed) {
         float* out = a.tt + (size_t)s * a.g.vol + ((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ);
         *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      // warp-level reduction of "what changed": travel times are >= 0, so float order == uint order
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(tmin));
+      if (lane == 0) {
+        atomicAdd(&S->units_run, 1ull);
+        if (wmin != 0x7f800000u) {
+          atomicAdd(&S->units_changed, 1ull);
+          atomicMin(&s_tmin, wmin);
+          atomicOr(&s_zmask, 1u << zc);
+        }
       }
     }
 
     // block-wide "anything changed" (also the barrier that ends all smem reads of this tile)
     const int any = __syncthreads_or(changed);
     if (any && tid < 27) {
+      // a changed node reaches R <= 7 cells: every x/y neighbour tile (8 wide) is affected, the
+      // z neighbours (32 long) only when the first / last z chunk changed
       const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
       const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-      if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
-        a.dirty[(size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz] = 1;
+      const unsigned zm = s_zmask;
+      const bool reach = (dz == 0) || (dz < 0 && (zm & 1u)) || (dz > 0 && (zm & (1u << (TZ / KZ - 1))));
+      if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
+        atomicMin(&a.key[(size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz], s_tmin);
     }
     if (tid == 32) {
       const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
@@ -428,13 +452,27 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
 // ---------------------------------------------------------------------------------------
 // work-list compaction + device-resident round bookkeeping
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_dirty(const RelaxArgs a, unsigned long long cond) {
+__global__ void __launch_bounds__(256) scan_min_key(const RelaxArgs a) {
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  unsigned m = 0x7f800000u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    m = min(m, a.key[i]);
+  m = __reduce_min_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(&a.st->kmin_bits, m);
+}
+
+__global__ void __launch_bounds__(256) select_tiles(const RelaxArgs a, unsigned long long cond) {
   SolveState* S = a.st;
   const int nxt = S->parity ^ 1;
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool set = (i < total) && a.dirty[i];
-  // warp-aggregated append
+  // bucket: keys within `bucket` of the smallest pending key (Dijkstra-like ordering at tile
+  // granularity; travel times below the bucket are final, so their tiles are not re-relaxed with
+  // inputs that are still going to change)
+  const float kmin = __uint_as_float(S->kmin_bits);
+  const unsigned thr = (a.bucket < 0.f) ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
+  const unsigned k = (i < total) ? a.key[i] : 0x7f800000u;
+  const bool set = (k != 0x7f800000u) && (k <= thr);
   const unsigned ballot = __ballot_sync(0xffffffffu, set);
   if (ballot) {
     const int lane = threadIdx.x & 31;
@@ -444,7 +482,7 @@ __global__ void __launch_bounds__(256) compact_dirty(const RelaxArgs a, unsigned
     base = __shfl_sync(0xffffffffu, base, leader);
     if (set) {
       a.worklist[(size_t)nxt * a.cap + base + __popc(ballot & ((1u << lane) - 1))] = (unsigned)i;
-      a.dirty[i] = 0;
+      a.key[i] = 0x7f800000u;
     }
   }
   // last block done: flip the lists and advance the round
@@ -460,9 +498,10 @@ __global__ void __launch_bounds__(256) compact_dirty(const RelaxArgs a, unsigned
     S->count[nxt ^ 1] = 0;
     S->parity = nxt;
     S->round += 1;
+    S->kmin_bits = 0x7f800000u;
 #if __CUDA_ARCH__ >= 900
     if (cond) {
-      const bool more = (S->last_changed_round == S->round) && (S->max_rounds == 0 || S->round < S->max_rounds);
+      const bool more = (S->count[nxt] != 0) && (S->max_rounds == 0 || S->round < S->max_rounds);
       cudaGraphSetConditional((cudaGraphConditionalHandle)cond, more ? 1u : 0u);
     }
 #endif
@@ -570,7 +609,8 @@ __global__ void pad_kernel(const float* __restrict__ dense, float* __restrict__ 
     const int z = (int)(i % g.nz);
     const long long r = i / g.nz;
     const int y = (int)(r % g.ny), x = (int)(r / g.ny);
-    padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)] = dense[i];
+    padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)] =
+        dense[x * g.dstride[0] + y * g.dstride[1] + z * g.dstride[2]];
   }
 }
 __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict__ dense, BoxGeom g) {
@@ -579,7 +619,8 @@ __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict
     const int z = (int)(i % g.nz);
     const long long r = i / g.nz;
     const int y = (int)(r % g.ny), x = (int)(r / g.ny);
-    dense[i] = padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)];
+    dense[x * g.dstride[0] + y * g.dstride[1] + z * g.dstride[2]] =
+        padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)];
   }
 }
 // one block per source: tt[start] = 0 and the 27 tiles around the start's tile go on list 0
@@ -686,7 +727,8 @@ cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow
 cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream) {
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
   const unsigned blocks = (unsigned)((total + 255) / 256);
-  compact_dirty<<<blocks, 256, 0, stream>>>(a, cond);
+  scan_min_key<<<std::min(blocks, 1184u), 256, 0, stream>>>(a);
+  select_tiles<<<blocks, 256, 0, stream>>>(a, cond);
   return cudaGetLastError();
 }
 
@@ -724,6 +766,7 @@ cudaError_t launch_unpad_box(const float* padded, float* dense, BoxGeom g, cudaS
 __global__ void init_state_kernel(SolveState* S, int max_rounds) {
   SolveState z = {};
   z.max_rounds = max_rounds;
+  z.kmin_bits = 0x7f800000u;
   *S = z;
 }
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {
@@ -731,7 +774,7 @@ cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream
   cudaError_t e = launch_fill(a.tt, (long long)a.nsrc * a.g.vol, std::numeric_limits<float>::infinity(), stream);
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
-  e = cudaMemsetAsync(a.dirty, 0, total, stream);
+  e = launch_fill(reinterpret_cast<float*>(a.key), (long long)((total + 3) / 4 * 4), std::numeric_limits<float>::infinity(), stream);
   if (e != cudaSuccess) return e;
   init_sources_kernel<<<a.nsrc, 32, 0, stream>>>(a);
   return cudaGetLastError();

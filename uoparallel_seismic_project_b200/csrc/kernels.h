@@ -36,7 +36,9 @@ struct RelaxArgs {
   SolveState* st;
   unsigned* worklist;          // 2 * cap entries
   unsigned cap;
-  unsigned char* dirty;        // nsrc * ntiles flags (marks for the next round)
+  unsigned* key;               // nsrc * ntiles activation keys: float bits of the smallest travel time
+                               // that changed next to the tile since it was last relaxed; INF = clean
+  float bucket;                // only tiles with key <= (smallest key) + bucket run in a round; <0 = all
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
@@ -45,8 +47,9 @@ struct RelaxArgs {
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow,
                                const CUtensorMap& tm_tt, const RelaxArgs& a, cudaStream_t stream);
-// Scans the dirty flags into the next work list, flips parity, advances the round and (when
-// cond != 0) sets the CUDA-graph WHILE condition to "changed in the round just finished".
+// Two launches: (1) min-reduce the activation keys, (2) move every tile whose key is within the
+// bucket of that minimum to the next work list (clearing its key), flip parity, advance the
+// round and (when cond != 0) set the CUDA-graph WHILE condition to "work list not empty".
 cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream);
 
 // Simple (verification / fallback) path: one thread per node and source, global memory.

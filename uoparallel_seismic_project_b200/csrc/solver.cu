@@ -136,7 +136,9 @@ struct sweeptt_ctx {
   SolveState* d_state = nullptr;
   SolveState* h_state = nullptr;  // pinned mirror
   unsigned* d_worklist = nullptr;
-  unsigned char* d_dirty = nullptr;
+  unsigned* d_key = nullptr;   // per-tile activation keys
+  float bucket = -1.f;         // bucket width in travel-time units (<0: relax every dirty tile each round)
+  double mean_slowness = 0;
   size_t tiles_cap = 0;  // nsrc*ntiles the lists/flags were sized for
   unsigned long long* d_tile_pulls = nullptr;
   unsigned long long* d_viol = nullptr;
@@ -240,7 +242,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   invalidate_graph(c);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
-  cudaFree(c->d_worklist); cudaFree(c->d_dirty); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
+  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -282,7 +284,27 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sweeptt_set_model: bad dimensions %d x %d x %d", nx, ny, nz);
   CK(cudaSetDevice(c->device));
   BoxGeom g{};
-  g.nx = nx; g.ny = ny; g.nz = nz;
+  {
+    // window axis (kernel z, tiled by TZ=32): the caller's z unless another axis wastes >25% fewer
+    // lanes.  (Measured on 241x241x51: windows along y raise lane efficiency 0.80 -> 0.94 but the
+    // coarser 32-long tiles along a long axis make the active-tile shell thicker: 61 ms vs 53 ms.)
+    const int n[3] = {nx, ny, nz};
+    int win = 2;
+    double best = -1;
+    for (int a = 2; a >= 0; --a) {  // ties keep the caller's z (no permutation)
+      const double eff = (double)n[a] / (double)(((n[a] + TZ - 1) / TZ) * TZ);
+      if (eff > best * (a == 2 ? 1.0 : 1.25)) { best = eff; win = a; }
+    }
+    if (const char* e = getenv("SWEEPTT_WINDOW_AXIS")) win = std::max(0, std::min(2, atoi(e)));
+    int q = 0;
+    for (int a = 0; a < 3; ++a)
+      if (a != win) g.perm[q++] = a;
+    g.perm[2] = win;
+    const long long ds[3] = {(long long)ny * nz, (long long)nz, 1};
+    for (int k = 0; k < 3; ++k) g.dstride[k] = ds[g.perm[k]];
+    g.nx = n[g.perm[0]]; g.ny = n[g.perm[1]]; g.nz = n[g.perm[2]];
+    nx = g.nx; ny = g.ny; nz = g.nz;  // from here on: kernel axis order
+  }
   g.ntx = (nx + TX - 1) / TX; g.nty = (ny + TY - 1) / TY; g.ntz = (nz + TZ - 1) / TZ;
   g.px = AX + g.ntx * TX + RXY_MAX;
   g.py = AY + g.nty * TY + RXY_MAX;
@@ -291,6 +313,7 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   g.vol = (long long)g.px * g.sx;
   if ((long long)g.ntx * g.nty * g.ntz > 0x7fffffffLL) return fail("grid too large for 32-bit tile ids");
   const bool same = c->have_model && c->g.px == g.px && c->g.py == g.py && c->g.pz == g.pz;
+  const bool perm_changed = !c->have_model || std::memcmp(c->g.perm, g.perm, sizeof g.perm) != 0;
   if (!same) {
     CK(cudaStreamSynchronize(c->stream));
     dev_free(c, c->d_slow, (size_t)c->g.vol * 4);
@@ -303,12 +326,31 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   }
   c->g = g;
   const size_t dense = (size_t)nx * ny * nz;
+  {
+    // mean slowness of a strided sample: only used to scale the activation bucket (scheduling,
+    // never the arithmetic)
+    double sum = 0;
+    size_t cnt = 0;
+    const size_t step = std::max<size_t>(1, dense / 65536);
+    for (size_t i = 0; i < dense; i += step) {
+      if (std::isfinite(slowness[i])) { sum += slowness[i]; ++cnt; }
+    }
+    c->mean_slowness = cnt ? sum / (double)cnt : 0.0;
+  }
   if (!ensure_stage(c, dense)) return 0;
   CK(launch_fill(c->d_slow, g.vol, std::numeric_limits<float>::infinity(), c->stream));
   CK(cudaMemcpyAsync(c->d_stage, slowness, dense * 4, cudaMemcpyHostToDevice, c->stream));
   CK(launch_pad_box(c->d_stage, c->d_slow, g, c->stream));
   c->have_model = true;
-  if (c->have_star && !build_tile_pulls(c)) return 0;
+  if (c->have_star) {
+    if (perm_changed) {  // the star tables are kept in kernel axis order
+      std::vector<FS> fs = c->fs;
+      if (!sweeptt_set_star(c, fs.data(), (int)fs.size())) return 0;
+    } else if (!build_tile_pulls(c)) {
+      return 0;
+    }
+  }
+  if (perm_changed) c->have_sources = false;
   return 1;
 }
 
@@ -363,8 +405,20 @@ extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsiz
   if (!c || !fs) return fail("sweeptt_set_star: null argument");
   if (starsize < 2) return fail("sweeptt_set_star: a forward star needs at least 2 entries (the last one is unused)");
   CK(cudaSetDevice(c->device));
-  c->fs.assign(fs, fs + starsize);
-  c->star = build_pull_star(fs, starsize, c->opts.star_used);
+  {
+    std::vector<FS> keep(fs, fs + starsize);  // (fs may alias c->fs)
+    c->fs.swap(keep);
+  }
+  {
+    // kernel axis order (identity until a model has been set; set_model re-runs this)
+    std::vector<FS> pf(c->fs);
+    if (c->have_model)
+      for (auto& e : pf) {
+        const int o[3] = {e.i, e.j, e.k};
+        e.i = o[c->g.perm[0]]; e.j = o[c->g.perm[1]]; e.k = o[c->g.perm[2]];
+      }
+    c->star = build_pull_star(pf.data(), starsize, c->opts.star_used);
+  }
   if (c->star.all.empty()) return fail("sweeptt_set_star: the star has no usable offsets");
   std::vector<StarDev> sd(c->star.all.size());
   for (size_t l = 0; l < sd.size(); ++l) {
@@ -505,11 +559,13 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
   if (numstart <= 0) return fail("sweeptt_set_sources: need at least one start point");
   CK(cudaSetDevice(c->device));
   const BoxGeom& g = c->g;
+  int on[3];  // caller-order dims
+  on[g.perm[0]] = g.nx; on[g.perm[1]] = g.ny; on[g.perm[2]] = g.nz;
   for (int s = 0; s < numstart; ++s)
-    if (starts[s].i < 0 || starts[s].i >= g.nx || starts[s].j < 0 || starts[s].j >= g.ny || starts[s].k < 0 ||
-        starts[s].k >= g.nz)
+    if (starts[s].i < 0 || starts[s].i >= on[0] || starts[s].j < 0 || starts[s].j >= on[1] || starts[s].k < 0 ||
+        starts[s].k >= on[2])
       return fail("start point %d (%d,%d,%d) is outside the %d x %d x %d model", s, starts[s].i, starts[s].j,
-                  starts[s].k, g.nx, g.ny, g.nz);
+                  starts[s].k, on[0], on[1], on[2]);
   CK(cudaStreamSynchronize(c->stream));
   if (numstart > c->tt_cap) {  // grow the pool
     dev_free(c, c->d_tt, (size_t)g.vol * 4 * c->tt_cap);
@@ -530,18 +586,19 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
   if (ntiles * numstart > 0xfffffff0ull) return fail("too many tiles (%zu x %d sources) for 32-bit work-list entries", ntiles, numstart);
   if (ntiles * numstart > c->tiles_cap) {
     dev_free(c, c->d_worklist, c->tiles_cap * 8);
-    dev_free(c, c->d_dirty, c->tiles_cap);
-    c->d_worklist = nullptr; c->d_dirty = nullptr;
+    dev_free(c, c->d_key, (c->tiles_cap + 4) * 4);
+    c->d_worklist = nullptr; c->d_key = nullptr;
     c->tiles_cap = ntiles * numstart;
     if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 8)) return 0;
-    if (!dev_alloc(c, (void**)&c->d_dirty, c->tiles_cap)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_key, (c->tiles_cap + 4) * 4)) return 0;
     invalidate_graph(c);
   }
   if (numstart != c->nsrc) invalidate_graph(c);
   c->nsrc = numstart;
   c->src_xyz.resize(3 * numstart);
   for (int s = 0; s < numstart; ++s) {
-    c->src_xyz[3 * s] = starts[s].i; c->src_xyz[3 * s + 1] = starts[s].j; c->src_xyz[3 * s + 2] = starts[s].k;
+    const int o[3] = {starts[s].i, starts[s].j, starts[s].k};
+    for (int q = 0; q < 3; ++q) c->src_xyz[3 * s + q] = o[g.perm[q]];
   }
   CK(cudaMemcpy(c->d_src, c->src_xyz.data(), sizeof(int) * 3 * numstart, cudaMemcpyHostToDevice));
   c->have_sources = true;
@@ -558,7 +615,8 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.st = c->d_state;
   a.worklist = c->d_worklist;
   a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
-  a.dirty = c->d_dirty;
+  a.key = c->d_key;
+  a.bucket = c->bucket;
   a.tile_pulls = c->d_tile_pulls;
   a.ncols = (int)c->dev_columns.size();
   a.nextra = (int)c->star.extra.size();
@@ -574,6 +632,13 @@ static int ready(sweeptt_ctx* c) {
   if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
     if (!build_maps(c)) return 0;
     if (!upload_constants(c)) return 0;
+    // activation bucket = factor x (delay of the longest star edge in a medium of mean slowness)
+    double factor = 1.0;
+    if (const char* e = getenv("SWEEPTT_BUCKET")) factor = atof(e);
+    float hdmax = 0.f;
+    for (const auto& p : c->star.all) hdmax = std::max(hdmax, p.hd);
+    const float b = (factor > 0 && c->mean_slowness > 0) ? (float)(factor * 2.0 * hdmax * c->mean_slowness) : -1.f;
+    if (b != c->bucket) { c->bucket = b; invalidate_graph(c); }
   }
   return 1;
 }
@@ -646,6 +711,8 @@ static void fill_stats(sweeptt_ctx* c, sweeptt_stats* st, int rounds_before, lon
   st->tile_visits = (long long)h.tile_visits;
   st->relaxations = (long long)h.pulls;
   st->relax_kernel_ms = relax_ms;
+  st->units_run = (long long)h.units_run;
+  st->units_changed = (long long)h.units_changed;
 }
 
 static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int* changed_out, sweeptt_stats* stats) {
@@ -673,7 +740,7 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
     CK(cudaGraphLaunch(c->graph_exec, c->stream));
     if (!read_state(c)) return 0;
     const int r = c->h_state->round - rounds_before;
-    launches = 2LL * r; relax_launches = r;
+    launches = (c->kernel_used == SWEEPTT_KERNEL_TILED ? 3LL : 2LL) * r; relax_launches = r;
   } else {
     const int per_poll = to_convergence ? (c->opts.rounds_per_poll > 0 ? c->opts.rounds_per_poll : 8) : fixed_rounds;
     size_t ev_used = 0;
@@ -695,7 +762,7 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
         if (profile) { CK(cudaEventRecord(c->prof_events[ev_used + 1], c->stream)); ev_used += 2; }
         if (c->kernel_used == SWEEPTT_KERNEL_TILED) { CK(launch_compact(a, 0, c->stream)); }
         else { CK(launch_advance_simple(c->d_state, 0, c->stream)); }
-        launches += 2; relax_launches += 1;
+        launches += (c->kernel_used == SWEEPTT_KERNEL_TILED ? 3 : 2); relax_launches += 1;
       }
       if (!read_state(c)) return 0;
       if (profile) {
@@ -708,13 +775,17 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
       }
       if (!to_convergence) break;
       const SolveState& h = *c->h_state;
-      if (h.last_changed_round < h.round) break;  // the last round changed nothing
+      const bool done = (c->kernel_used == SWEEPTT_KERNEL_TILED) ? (h.count[h.parity] == 0)  // nothing left to relax
+                                                                  : (h.last_changed_round < h.round);
+      if (done) break;
       if (c->opts.max_rounds > 0 && h.round - rounds_before >= c->opts.max_rounds) break;
       if (c->opts.verbose > 0)
         fprintf(stderr, "[sweeptt] round %d: %u tiles queued, %llu pulls so far\n", h.round, h.count[h.parity], h.pulls);
     }
   }
-  if (changed_out) *changed_out = c->h_state->last_changed_round == c->h_state->round;
+  if (changed_out)
+    *changed_out = (c->kernel_used == SWEEPTT_KERNEL_TILED) ? (c->h_state->count[c->h_state->parity] != 0)
+                                                            : (c->h_state->last_changed_round == c->h_state->round);
   fill_stats(c, stats, rounds_before, launches, relax_launches, relax_ms);
   return 1;
 }
@@ -772,7 +843,7 @@ extern "C" int sweeptt_put_tt(sweeptt_ctx* c, int s, const float* in) {
   // every tile of this source must be looked at again
   // (the pending work list is replaced, so mark every source's tiles, not only this one's)
   const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
-  CK(cudaMemsetAsync(c->d_dirty, 1, ntiles * c->nsrc, c->stream));
+  CK(cudaMemsetAsync(c->d_key, 0, ntiles * c->nsrc * 4, c->stream));  // key 0.0 = relax now
   CK(launch_compact(make_args(c), 0, c->stream));  // folds the marks into the next work list
   CK(cudaStreamSynchronize(c->stream));
   return 1;
@@ -911,6 +982,8 @@ extern "C" int sweeptt_solve(const float* slowness, int nx, int ny, int nz, cons
       total.d2h_ms = std::max(total.d2h_ms, st[d].d2h_ms);
       total.h2d_bytes += st[d].h2d_bytes;
       total.d2h_bytes += st[d].d2h_bytes;
+      total.units_run += st[d].units_run;
+      total.units_changed += st[d].units_changed;
     }
   }
   total.devices_used = ndev;
