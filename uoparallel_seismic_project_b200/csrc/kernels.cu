@@ -234,19 +234,27 @@ __device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const 
                                             int cbeg, int cend, const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
                                             const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
   constexpr uint32_t GM = granules_of(KMASK);
-  // the host pads every pattern group to an EVEN number of columns (a duplicated column is
-  // harmless: min is idempotent), so the ping-pong loop needs no tail copy of the code
+  constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
+  // Host-side guarantees (solver.cu, upload_constants): every pattern group has an EVEN number of
+  // columns (a duplicated column is harmless: min is idempotent), the half-distances of a group
+  // are contiguous in column order, and the table has two valid spare entries at its end -- so
+  // the loop needs no tail code, hd addresses are pure arithmetic, and the column descriptors
+  // can be fetched two columns ahead of the window loads that need them (software pipeline:
+  // LDC descriptor -> LDS windows -> packed FP, each stage one column apart).
   if (cbeg >= cend) return;
   float Wa[WIN], Ta[WIN], Wb[WIN], Tb[WIN];
-  ColumnDev ca = c_cols[cbeg];
-  load_window<GM>(sv + b0 + ca.soff, st + b0 + ca.soff, Wa, Ta);
+  int hi = c_cols[cbeg].hd_begin;
+  int soffA = c_cols[cbeg].soff;
+  int soffB = c_cols[cbeg + 1].soff;
+  load_window<GM>(sv + b0 + soffA, st + b0 + soffA, Wa, Ta);
   for (int c = cbeg; c < cend; c += 2) {
-    const ColumnDev cb = c_cols[c + 1];
-    load_window<GM>(sv + b0 + cb.soff, st + b0 + cb.soff, Wb, Tb);
-    relax_column<KMASK>(Wa, Ta, ca.hd_begin, vn, vnE, vnO, nz2, acc);
-    ca = c_cols[(c + 2 < cend) ? c + 2 : c];
-    load_window<GM>(sv + b0 + ca.soff, st + b0 + ca.soff, Wa, Ta);
-    relax_column<KMASK>(Wb, Tb, cb.hd_begin, vn, vnE, vnO, nz2, acc);
+    load_window<GM>(sv + b0 + soffB, st + b0 + soffB, Wb, Tb);
+    soffA = c_cols[c + 2].soff;
+    soffB = c_cols[c + 3].soff;
+    relax_column<KMASK>(Wa, Ta, hi, vn, vnE, vnO, nz2, acc);
+    load_window<GM>(sv + b0 + soffA, st + b0 + soffA, Wa, Ta);
+    relax_column<KMASK>(Wb, Tb, hi + NK, vn, vnE, vnO, nz2, acc);
+    hi += 2 * NK;
   }
 }
 

@@ -442,7 +442,7 @@ extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsiz
 static int choose_kernel(sweeptt_ctx* c) {
   const int want = c->opts.kernel;
   int rxy = 0;
-  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() + MAX_PATTERNS <= MAX_COLUMNS + 0 &&
+  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() + MAX_PATTERNS + 2 <= MAX_COLUMNS && 2 * (int)c->star.col_hd.size() <= MAX_COL_HD &&
                     (int)c->star.col_hd.size() <= MAX_COL_HD && (int)c->star.extra.size() <= MAX_EXTRA;
   if (fits) rxy = tiled_variant_for_radius(std::max(c->star.rx, c->star.ry));
   if (want == SWEEPTT_KERNEL_SIMPLE || (want == SWEEPTT_KERNEL_AUTO && rxy == 0)) {
@@ -493,19 +493,28 @@ static int upload_constants(sweeptt_ctx* c) {
   if (it != g_const_owner.end() && it->second == c && c->consts_rxy == c->tl.rxy) return 1;
   int sxd, syd, szd;
   tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
-  std::vector<ColumnDev> cols(c->dev_columns.size());
-  for (size_t i = 0; i < cols.size(); ++i) {
+  // columns in upload order (pattern-sorted, even-padded); half-distances re-packed in the same
+  // order so that a pattern group's hd values are contiguous; two spare entries at the end
+  std::vector<ColumnDev> cols(c->dev_columns.size() + 2);
+  std::vector<float> hd_packed;
+  for (size_t i = 0; i < c->dev_columns.size(); ++i) {
     const PullColumn& pc = c->dev_columns[i];
     ColumnDev d;
     d.soff = pc.i * syd * szd + pc.j * szd;
     d.kmask = pc.kmask;
-    d.hd_begin = pc.hd_begin;
+    d.hd_begin = (int)hd_packed.size();
     d.gmask = 0;
+    int nk = 0;
     for (int b = 0; b <= 2 * ZHALO; ++b)
-      if (pc.kmask & (1u << b))
+      if (pc.kmask & (1u << b)) {
+        hd_packed.push_back(c->star.col_hd[pc.hd_begin + nk++]);
         for (int k = 0; k < KZ; ++k) d.gmask |= 1u << ((k + b) / 4);
+      }
     cols[i] = d;
   }
+  cols[cols.size() - 2] = cols[cols.size() - 1] = cols[c->dev_columns.size() - 1];
+  if ((int)hd_packed.size() > MAX_COL_HD || (int)cols.size() > MAX_COLUMNS)
+    return fail("star tables exceed the __constant__ budget (%zu half-distances, %zu columns)", hd_packed.size(), cols.size());
   std::vector<ExtraDev> ex(c->star.extra.size());
   for (size_t i = 0; i < ex.size(); ++i) {
     const PullOffset& p = c->star.extra[i];
@@ -513,7 +522,7 @@ static int upload_constants(sweeptt_ctx* c) {
   }
   // a different context may still be running with the old tables on another stream
   if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
-  CK(upload_star_constants(cols.data(), (int)cols.size(), c->star.col_hd.data(), (int)c->star.col_hd.size(), ex.data(),
+  CK(upload_star_constants(cols.data(), (int)cols.size(), hd_packed.data(), (int)hd_packed.size(), ex.data(),
                            (int)ex.size(), c->stream));
   CK(cudaStreamSynchronize(c->stream));  // host vectors die here
   g_const_owner[c->device] = c;
