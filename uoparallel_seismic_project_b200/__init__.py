@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     load_library,
     make_star,
     solve,
+    solve_slabs,
     star_load,
     starts_load,
     text_load,

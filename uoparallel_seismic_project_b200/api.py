@@ -229,6 +229,25 @@ def solve(slowness, star, starts, *, delta: float = 10.0, out=None, device: int 
     return out, SweepStats._from(s)
 
 
+def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, delta: float = 10.0,
+                max_rounds: int | None = None, verbose: int | None = None):
+    """ONE source on ONE grid decomposed into `num_slabs` 1-D slabs over the visible GPUs (slabs share
+    devices round-robin when there are more slabs than GPUs), halo planes min-merged over NVLink
+    peer access after every local convergence.  Replaces the MPI ghost-cell programs
+    (mpi/16partsmpi.c:740-909).  Returns (tt float32[nx,ny,nz], SweepStats)."""
+    lib = load_library()
+    v = np.ascontiguousarray(slowness, dtype=np.float32)
+    nx, ny, nz = v.shape
+    fs = _as_star(star, delta)
+    st = START(int(start[0]), int(start[1]), int(start[2]))
+    out = np.empty(v.shape, np.float32)
+    o = _opts(num_devices=num_slabs, slab_axis=slab_axis, max_rounds=max_rounds, verbose=verbose)
+    s = _Stats()
+    _check(lib.sweeptt_solve_slabs(v.ctypes.data, nx, ny, nz, fs, len(fs), st, out.ctypes.data, C.byref(o), C.byref(s)),
+           "sweeptt_solve_slabs")
+    return out, SweepStats._from(s)
+
+
 def solve_raw(v_ptr: int, dims, fs, starts_arr, out_ptrs, opts: _Opts):
     """Pointer-level call for bench.py's e2e leg (pinned torch tensors; no numpy in the way)."""
     lib = load_library()

@@ -635,6 +635,7 @@ __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict
 __global__ void init_sources_kernel(const RelaxArgs a) {
   const int s = blockIdx.x;
   const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+  if (px < 0 || px >= a.g.nx || py < 0 || py >= a.g.ny || pz < 0 || pz >= a.g.nz) return;  // start owned by another slab
   if (threadIdx.x == 31)
     a.tt[(size_t)s * a.g.vol + ((size_t)(px + AX) * a.g.py + (py + AY)) * a.g.pz + (pz + AZ)] = 0.0f;
   if (threadIdx.x < 27) {
@@ -646,6 +647,55 @@ __global__ void init_sources_kernel(const RelaxArgs a) {
       a.worklist[pos] = s * ntiles + (ux * a.g.nty + uy) * a.g.ntz + uz;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// slab decomposition: min-merge the neighbour's boundary planes into our halo planes
+// (replaces the MPI ghost exchange, mpi/16partsmpi.c:760-900; min instead of overwrite keeps
+// every value a valid, monotonically decreasing upper bound)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_halo_kernel(const RelaxArgs a, const float* __restrict__ peer_tt,
+                                                         BoxGeom pg, int axis, int lo, int n, int peer_lo,
+                                                         unsigned* changed_flag) {
+  // planes [lo, lo+n) of kernel axis `axis` in OUR box correspond to planes [peer_lo, peer_lo+n) in the peer's
+  const int d[3] = {a.g.nx, a.g.ny, a.g.nz};
+  int ext[3] = {d[0], d[1], d[2]};
+  ext[axis] = n;
+  const long long total = (long long)ext[0] * ext[1] * ext[2];
+  const int ntiles = a.g.ntx * a.g.nty * a.g.ntz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c[3];
+    c[2] = (int)(i % ext[2]);
+    const long long r = i / ext[2];
+    c[1] = (int)(r % ext[1]);
+    c[0] = (int)(r / ext[1]);
+    int pc[3] = {c[0], c[1], c[2]};
+    c[axis] += lo;
+    pc[axis] += peer_lo;
+    const size_t mine = ((size_t)(c[0] + AX) * a.g.py + (c[1] + AY)) * a.g.pz + (c[2] + AZ);
+    const size_t theirs = ((size_t)(pc[0] + AX) * pg.py + (pc[1] + AY)) * pg.pz + (pc[2] + AZ);
+    const float v = peer_tt[theirs];  // peer memory over NVLink (or local when slabs share a device)
+    if (v < a.tt[mine]) {
+      a.tt[mine] = v;
+      *changed_flag = 1u;
+      const int tx = c[0] / TX, ty = c[1] / TY, tz = c[2] / TZ;
+      const unsigned bits = __float_as_uint(v);
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dz = -1; dz <= 1; ++dz) {
+            const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
+            if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
+              atomicMin(&a.key[((size_t)ux * a.g.nty + uy) * a.g.ntz + uz], bits);
+          }
+    }
+  }
+  (void)ntiles;
+}
+
+cudaError_t launch_merge_halo(const RelaxArgs& a, const float* peer_tt, const BoxGeom& peer_geom, int axis, int lo,
+                              int n, int peer_lo, unsigned* changed_flag, cudaStream_t stream) {
+  merge_halo_kernel<<<1184, 256, 0, stream>>>(a, peer_tt, peer_geom, axis, lo, n, peer_lo, changed_flag);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------

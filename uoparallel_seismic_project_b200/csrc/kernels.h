@@ -57,6 +57,11 @@ cudaError_t launch_relax_simple(const RelaxArgs& a, const StarDev* star, int nst
                                 unsigned long long pulls_per_round, cudaStream_t stream);
 cudaError_t launch_advance_simple(SolveState* st, unsigned long long cond, cudaStream_t stream);
 
+// Slab decomposition: tt[planes lo..lo+n of kernel axis] = min(own, peer's planes peer_lo..); marks
+// the tiles around every lowered node; *changed_flag |= 1 when anything was lowered.
+cudaError_t launch_merge_halo(const RelaxArgs& a, const float* peer_tt, const BoxGeom& peer_geom, int axis, int lo,
+                              int n, int peer_lo, unsigned* changed_flag, cudaStream_t stream);
+
 // Fixed-point verifier.
 cudaError_t launch_count_violations(const RelaxArgs& a, int source, const StarDev* star, int nstar,
                                     unsigned long long* out, cudaStream_t stream);

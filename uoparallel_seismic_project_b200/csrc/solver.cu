@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -164,11 +165,14 @@ struct sweeptt_ctx {
   bool graph_valid = false;
 
   std::vector<cudaEvent_t> prof_events;
+  bool allow_outside_sources = false;  // slab contexts: the start may lie in another slab
+  int force_window_axis = -1;          // slab contexts: all slabs must share one axis order
 };
 
 // the __constant__ star tables are per-device module state: remember which context owns them
 static std::mutex g_const_mu;
 static std::map<int, sweeptt_ctx*> g_const_owner;
+static std::map<int, uint64_t> g_const_sig;  // content hash of the tables currently in __constant__ memory
 
 static void invalidate_graph(sweeptt_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -237,7 +241,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   {
     std::lock_guard<std::mutex> lk(g_const_mu);
     auto it = g_const_owner.find(c->device);
-    if (it != g_const_owner.end() && it->second == c) g_const_owner.erase(it);
+    if (it != g_const_owner.end() && it->second == c) { g_const_owner.erase(it); g_const_sig.erase(c->device); }
   }
   invalidate_graph(c);
   for (auto e : c->prof_events) cudaEventDestroy(e);
@@ -296,6 +300,7 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
       if (eff > best * (a == 2 ? 1.0 : 1.25)) { best = eff; win = a; }
     }
     if (const char* e = getenv("SWEEPTT_WINDOW_AXIS")) win = std::max(0, std::min(2, atoi(e)));
+    if (c->force_window_axis >= 0) win = c->force_window_axis;
     int q = 0;
     for (int a = 0; a < 3; ++a)
       if (a != win) g.perm[q++] = a;
@@ -520,6 +525,22 @@ static int upload_constants(sweeptt_ctx* c) {
     const PullOffset& p = c->star.extra[i];
     ex[i] = ExtraDev{p.i, p.j, p.k, p.i * syd * szd + p.j * szd + p.k, p.hd, p.guarded, 0, 0};
   }
+  // identical tables already resident (e.g. several slab contexts sharing one device)?
+  uint64_t sig = 1469598103934665603ull;
+  auto mix = [&sig](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
+  };
+  mix(cols.data(), cols.size() * sizeof(ColumnDev));
+  mix(hd_packed.data(), hd_packed.size() * sizeof(float));
+  mix(ex.data(), ex.size() * sizeof(ExtraDev));
+  auto sg = g_const_sig.find(c->device);
+  if (sg != g_const_sig.end() && sg->second == sig && it != g_const_owner.end()) {
+    g_const_owner[c->device] = c;
+    c->consts_rxy = c->tl.rxy;
+    return 1;
+  }
+  g_const_sig[c->device] = sig;
   // a different context may still be running with the old tables on another stream
   if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
   CK(upload_star_constants(cols.data(), (int)cols.size(), hd_packed.data(), (int)hd_packed.size(), ex.data(),
@@ -570,7 +591,7 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
   const BoxGeom& g = c->g;
   int on[3];  // caller-order dims
   on[g.perm[0]] = g.nx; on[g.perm[1]] = g.ny; on[g.perm[2]] = g.nz;
-  for (int s = 0; s < numstart; ++s)
+  for (int s = 0; s < numstart && !c->allow_outside_sources; ++s)
     if (starts[s].i < 0 || starts[s].i >= on[0] || starts[s].j < 0 || starts[s].j >= on[1] || starts[s].k < 0 ||
         starts[s].k >= on[2])
       return fail("start point %d (%d,%d,%d) is outside the %d x %d x %d model", s, starts[s].i, starts[s].j,
@@ -1000,7 +1021,176 @@ extern "C" int sweeptt_solve(const float* slowness, int nx, int ny, int nz, cons
   return 1;
 }
 
-extern "C" int sweeptt_solve_slabs(const float*, int, int, int, const struct FS*, int, struct START, float*,
-                                   const sweeptt_opts*, sweeptt_stats*) {
-  return fail("sweeptt_solve_slabs: slab decomposition is not built yet (SURVEY.md §8e, config 5)");
+// ---------------------------------------------------------------------------------------
+// single huge grid: 1-D slab decomposition over the devices of one box
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Slab {
+  sweeptt_ctx* ctx = nullptr;
+  int device = 0;
+  int lo = 0, hi = 0;    // owned planes [lo,hi) of the slab axis (caller coordinates)
+  int blo = 0, bhi = 0;  // planes held = owned + halo
+  unsigned* d_flag = nullptr;
+  sweeptt_stats st{};
+  int ok = 1;
+  std::string err;
+};
+}  // namespace
+
+extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz, const struct FS* fs, int starsize,
+                                   struct START start, float* tt_out, const sweeptt_opts* opts, sweeptt_stats* stats) {
+  if (!slowness || !fs || !tt_out) return fail("sweeptt_solve_slabs: null argument");
+  sweeptt_opts o{};
+  if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof o, opts->struct_size > 0 ? opts->struct_size : sizeof o));
+  const int ndev = sweeptt_device_count();
+  if (ndev <= 0) return fail("no CUDA device available: the sweep has no CPU fallback");
+  const int G = std::max(1, o.num_devices);  // slabs; more slabs than devices share devices round-robin
+  const int axis = o.slab_axis;
+  if (axis < 0 || axis > 2) return fail("slab_axis must be 0 (x), 1 (y) or 2 (z)");
+  const int n[3] = {nx, ny, nz};
+  if (start.i < 0 || start.i >= nx || start.j < 0 || start.j >= ny || start.k < 0 || start.k >= nz)
+    return fail("start point (%d,%d,%d) is outside the %d x %d x %d model", start.i, start.j, start.k, nx, ny, nz);
+  if (G > n[axis]) return fail("more slabs (%d) than planes (%d) along the slab axis", G, n[axis]);
+  int R = 0;  // ghost width = star radius along the slab axis (mpi/16partsmpi.c:65 `ghostcell`)
+  for (int l = 0; l < starsize; ++l) R = std::max(R, std::abs(axis == 0 ? fs[l].i : axis == 1 ? fs[l].j : fs[l].k));
+  const size_t stride[3] = {(size_t)ny * nz, (size_t)nz, 1};
+
+  std::vector<Slab> slabs(G);
+  auto cleanup = [&] {
+    for (auto& sl : slabs) {
+      if (sl.d_flag) { cudaSetDevice(sl.device); cudaFree(sl.d_flag); }
+      if (sl.ctx) sweeptt_destroy(sl.ctx);
+    }
+  };
+  // ---- build one context per slab: sub-box of the model + halo planes --------------------------
+  for (int d = 0; d < G; ++d) {
+    Slab& sl = slabs[d];
+    sl.device = d % ndev;
+    sl.lo = (int)((long long)n[axis] * d / G);
+    sl.hi = (int)((long long)n[axis] * (d + 1) / G);
+    sl.blo = std::max(0, sl.lo - R);
+    sl.bhi = std::min(n[axis], sl.hi + R);
+    sweeptt_opts so = o;
+    so.device = sl.device;
+    so.num_devices = 1;
+    sl.ctx = sweeptt_create(&so);
+    if (!sl.ctx) { cleanup(); return 0; }
+    sl.ctx->allow_outside_sources = true;
+    sl.ctx->force_window_axis = 2;  // every slab keeps the caller's axis order
+    int sub[3] = {nx, ny, nz};
+    sub[axis] = sl.bhi - sl.blo;
+    std::vector<float> box((size_t)sub[0] * sub[1] * sub[2]);
+    for (int x = 0; x < sub[0]; ++x)
+      for (int y = 0; y < sub[1]; ++y) {
+        const int gx = x + (axis == 0 ? sl.blo : 0), gy = y + (axis == 1 ? sl.blo : 0), gz = (axis == 2 ? sl.blo : 0);
+        std::memcpy(&box[((size_t)x * sub[1] + y) * sub[2]], slowness + gx * stride[0] + gy * stride[1] + gz,
+                    sizeof(float) * sub[2]);
+      }
+    START local = start;
+    (axis == 0 ? local.i : axis == 1 ? local.j : local.k) -= sl.blo;
+    if (!sweeptt_set_model(sl.ctx, box.data(), sub[0], sub[1], sub[2]) || !sweeptt_set_star(sl.ctx, fs, starsize) ||
+        !sweeptt_set_sources(sl.ctx, &local, 1) || !sweeptt_reset(sl.ctx)) {
+      cleanup();
+      return 0;
+    }
+    if (sl.ctx->kernel_used != SWEEPTT_KERNEL_TILED) {
+      cleanup();
+      return fail("slab decomposition needs the tiled kernel (star too wide for its halo)");
+    }
+    if (cudaMalloc(&sl.d_flag, sizeof(unsigned)) != cudaSuccess) { cleanup(); return fail("cudaMalloc failed"); }
+  }
+  // ---- peer access between neighbouring slabs on different devices (NVLink P2P) ------------------
+  for (int d = 0; d + 1 < G; ++d) {
+    const int a = slabs[d].device, b = slabs[d + 1].device;
+    if (a == b) continue;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, a, b);
+    if (!can) { cleanup(); return fail("devices %d and %d cannot access each other's memory", a, b); }
+    cudaSetDevice(a); if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
+    cudaSetDevice(b); if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
+  }
+
+  // ---- outer loop: local convergence on every slab, then halo exchange -------------------------
+  sweeptt_stats total{};
+  total.struct_size = sizeof total;
+  const auto t0 = std::chrono::steady_clock::now();
+  int outer = 0;
+  for (;; ++outer) {
+    std::vector<std::thread> th;
+    for (int d = 0; d < G; ++d)
+      th.emplace_back([&, d] {
+        Slab& sl = slabs[d];
+        if (cudaSetDevice(sl.device) != cudaSuccess) { sl.ok = 0; sl.err = "cudaSetDevice failed"; return; }
+        int changed = 0;
+        sl.ok = run_rounds(sl.ctx, true, 0, &changed, &sl.st);
+        if (!sl.ok) sl.err = g_err;
+      });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < G; ++d)
+      if (!slabs[d].ok) { const std::string e = slabs[d].err; cleanup(); return fail("slab %d: %s", d, e.c_str()); }
+    // exchange: each side min-merges the neighbour's owned boundary planes into its halo
+    for (int d = 0; d < G; ++d) {
+      cudaSetDevice(slabs[d].device);
+      CK(cudaMemsetAsync(slabs[d].d_flag, 0, sizeof(unsigned), slabs[d].ctx->stream));
+    }
+    for (int d = 0; d + 1 < G; ++d) {
+      Slab& A = slabs[d];      // owns planes below the interface at A.hi == B.lo
+      Slab& B = slabs[d + 1];
+      const int up = A.bhi - A.hi;   // A's halo planes above the interface (owned by B)
+      const int dn = B.lo - B.blo;   // B's halo planes below the interface (owned by A)
+      if (up > 0) {
+        cudaSetDevice(A.device);
+        CK(launch_merge_halo(make_args(A.ctx), B.ctx->d_tt, B.ctx->g, axis, A.hi - A.blo, up, A.hi - B.blo, A.d_flag,
+                             A.ctx->stream));
+      }
+      if (dn > 0) {
+        cudaSetDevice(B.device);
+        CK(launch_merge_halo(make_args(B.ctx), A.ctx->d_tt, A.ctx->g, axis, 0, dn, B.blo - A.blo, B.d_flag,
+                             B.ctx->stream));
+      }
+    }
+    unsigned any = 0;
+    for (int d = 0; d < G; ++d) {
+      unsigned f = 0;
+      cudaSetDevice(slabs[d].device);
+      CK(cudaMemcpyAsync(&f, slabs[d].d_flag, sizeof f, cudaMemcpyDeviceToHost, slabs[d].ctx->stream));
+      CK(cudaStreamSynchronize(slabs[d].ctx->stream));
+      any |= f;
+    }
+    if (o.verbose > 0) fprintf(stderr, "[sweeptt] slab exchange %d: %s\n", outer, any ? "halos lowered" : "no change");
+    if (!any) break;  // no halo changed after every slab had converged locally: global fixed point
+    if (o.max_rounds > 0 && outer >= o.max_rounds) { cleanup(); return fail("slabs not converged after %d exchanges", outer); }
+  }
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+  // ---- gather the owned planes --------------------------------------------------------------------
+  for (int d = 0; d < G; ++d) {
+    Slab& sl = slabs[d];
+    int sub[3] = {nx, ny, nz};
+    sub[axis] = sl.bhi - sl.blo;
+    std::vector<float> box((size_t)sub[0] * sub[1] * sub[2]);
+    cudaSetDevice(sl.device);
+    if (!sweeptt_get_tt(sl.ctx, 0, box.data())) { cleanup(); return 0; }
+    for (int x = 0; x < sub[0]; ++x)
+      for (int y = 0; y < sub[1]; ++y) {
+        const int gx = x + (axis == 0 ? sl.blo : 0), gy = y + (axis == 1 ? sl.blo : 0);
+        if ((axis == 0 && (gx < sl.lo || gx >= sl.hi)) || (axis == 1 && (gy < sl.lo || gy >= sl.hi))) continue;
+        const int z0 = axis == 2 ? sl.lo - sl.blo : 0, zn = axis == 2 ? sl.hi - sl.lo : sub[2];
+        std::memcpy(tt_out + gx * stride[0] + gy * stride[1] + (axis == 2 ? sl.lo : 0),
+                    &box[((size_t)x * sub[1] + y) * sub[2] + z0], sizeof(float) * zn);
+      }
+    // the context counters are cumulative since the reset: read the final totals
+    read_state(sl.ctx);
+    total.relaxations += (long long)sl.ctx->h_state->pulls;
+    total.tile_visits += (long long)sl.ctx->h_state->tile_visits;
+    total.rounds = std::max(total.rounds, sl.ctx->h_state->round);
+    total.kernel_launches += 3LL * sl.ctx->h_state->round + 2LL * (outer + 1);
+    total.relax_launches += sl.ctx->h_state->round;
+  }
+  total.kernel_used = SWEEPTT_KERNEL_TILED;
+  total.devices_used = std::min(G, ndev);
+  total.solve_ms = ms;
+  if (stats) *stats = total;
+  cleanup();
+  return 1;
 }
