@@ -541,8 +541,9 @@ __device__ __forceinline__ float pull_min_global(const RelaxArgs& a, const float
 __global__ void __launch_bounds__(128) relax_simple(const RelaxArgs a, const StarDev* __restrict__ star, int nstar,
                                                     unsigned long long pulls_per_round) {
   // z fastest across threads -> coalesced
-  const int z = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y % a.g.ny, x = blockIdx.y / a.g.ny;
+  // grid.x = nx*ny columns (up to 2^31-1), grid.y = z blocks, grid.z = sources
+  const int z = blockIdx.y * blockDim.x + threadIdx.x;
+  const int y = blockIdx.x % a.g.ny, x = blockIdx.x / a.g.ny;
   const int s = blockIdx.z;
   int changed = 0;
   if (z < a.g.nz) {
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(128) relax_simple(const RelaxArgs a, const Sta
     }
   }
   if (__syncthreads_or(changed) && threadIdx.x == 0) atomicMax(&a.st->last_changed_round, a.st->round + 1);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&a.st->pulls, pulls_per_round);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) atomicAdd(&a.st->pulls, pulls_per_round);
 }
 
 __global__ void advance_simple(SolveState* S, unsigned long long cond) {
@@ -575,8 +576,8 @@ __global__ void advance_simple(SolveState* S, unsigned long long cond) {
 __global__ void __launch_bounds__(128) count_violations_kernel(const RelaxArgs a, int s,
                                                                const StarDev* __restrict__ star, int nstar,
                                                                unsigned long long* out) {
-  const int z = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y % a.g.ny, x = blockIdx.y / a.g.ny;
+  const int z = blockIdx.y * blockDim.x + threadIdx.x;
+  const int y = blockIdx.x % a.g.ny, x = blockIdx.x / a.g.ny;
   unsigned bad = 0;
   if (z < a.g.nz) {
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
@@ -792,7 +793,7 @@ cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStre
 
 cudaError_t launch_relax_simple(const RelaxArgs& a, const StarDev* star, int nstar,
                                 unsigned long long pulls_per_round, cudaStream_t stream) {
-  dim3 grid((a.g.nz + 127) / 128, a.g.nx * a.g.ny, a.nsrc);
+  dim3 grid(a.g.nx * a.g.ny, (a.g.nz + 127) / 128, a.nsrc);
   relax_simple<<<grid, 128, 0, stream>>>(a, star, nstar, pulls_per_round);
   return cudaGetLastError();
 }
@@ -803,7 +804,7 @@ cudaError_t launch_advance_simple(SolveState* st, unsigned long long cond, cudaS
 
 cudaError_t launch_count_violations(const RelaxArgs& a, int source, const StarDev* star, int nstar,
                                     unsigned long long* out, cudaStream_t stream) {
-  dim3 grid((a.g.nz + 127) / 128, a.g.nx * a.g.ny, 1);
+  dim3 grid(a.g.nx * a.g.ny, (a.g.nz + 127) / 128, 1);
   count_violations_kernel<<<grid, 128, 0, stream>>>(a, source, star, nstar, out);
   return cudaGetLastError();
 }
