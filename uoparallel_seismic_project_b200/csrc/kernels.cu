@@ -783,8 +783,77 @@ cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow
   return cudaGetLastError();
 }
 
+// Small problems (<= 64 Ki tiles): ONE block does the min-scan, the selection AND orders the
+// selected tiles by activation key (counting sort into 32 key bins), so the persistent relaxation
+// CTAs pop tiles in increasing travel-time order -- later tiles of a round then read what earlier
+// ones produced (Gauss-Seidel along the propagation direction) -- and a round is one launch shorter.
+constexpr int FUSED_MAX_KEYS = 65536;
+constexpr int FUSED_BINS = 32;
+__global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigned long long cond) {
+  __shared__ unsigned s_min;
+  __shared__ unsigned s_bin[FUSED_BINS + 1];
+  SolveState* S = a.st;
+  const int nxt = S->parity ^ 1;
+  const unsigned total = (unsigned)((size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz);
+  if (threadIdx.x == 0) s_min = 0x7f800000u;
+  if (threadIdx.x <= FUSED_BINS) s_bin[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned m = 0x7f800000u;
+  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) m = min(m, a.key[i]);
+  m = __reduce_min_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(&s_min, m);
+  __syncthreads();
+  const float kmin = __uint_as_float(s_min);
+  const bool all = a.bucket < 0.f;
+  const unsigned thr = all ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
+  const float scale = all ? 0.f : (float)FUSED_BINS / a.bucket;
+  // pass A: histogram of the selected tiles' key bins
+  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) {
+    const unsigned k = a.key[i];
+    if (k != 0x7f800000u && k <= thr) {
+      const int b = min(FUSED_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
+      atomicAdd(&s_bin[b + 1], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int b = 0; b < FUSED_BINS; ++b) s_bin[b + 1] += s_bin[b];  // exclusive starts in s_bin[0..BINS-1]
+  __syncthreads();
+  const unsigned cnt = s_bin[FUSED_BINS];
+  __syncthreads();
+  // pass B: scatter in bin order, clear the keys
+  unsigned* wl = a.worklist + (size_t)nxt * a.cap;
+  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) {
+    const unsigned k = a.key[i];
+    if (k != 0x7f800000u && k <= thr) {
+      const int b = min(FUSED_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
+      wl[atomicAdd(&s_bin[b], 1u)] = i;
+      a.key[i] = 0x7f800000u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    S->cursor = 0;
+    S->count[nxt] = cnt;
+    S->count[nxt ^ 1] = 0;
+    S->parity = nxt;
+    S->round += 1;
+    S->kmin_bits = 0x7f800000u;
+#if __CUDA_ARCH__ >= 900
+    if (cond) {
+      const bool more = (cnt != 0) && (S->max_rounds == 0 || S->round < S->max_rounds);
+      cudaGraphSetConditional((cudaGraphConditionalHandle)cond, more ? 1u : 0u);
+    }
+#endif
+  }
+}
+
 cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream) {
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  if (total <= (size_t)FUSED_MAX_KEYS) {
+    compact_fused<<<1, 1024, 0, stream>>>(a, cond);
+    return cudaGetLastError();
+  }
   const unsigned blocks = (unsigned)((total + 255) / 256);
   scan_min_key<<<std::min(blocks, 1184u), 256, 0, stream>>>(a);
   select_tiles<<<blocks, 256, 0, stream>>>(a, cond);
