@@ -612,6 +612,10 @@ __global__ void fill_kernel(float4* p, long long n4, float value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
     p[i] = v;
 }
+__global__ void fill_u32_kernel(unsigned* p, long long n, unsigned value) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = value;
+}
 __global__ void pad_kernel(const float* __restrict__ dense, float* __restrict__ padded, BoxGeom g) {
   const long long vol = (long long)g.nx * g.ny * g.nz;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += (long long)gridDim.x * blockDim.x) {
@@ -897,12 +901,18 @@ __global__ void init_state_kernel(SolveState* S, int max_rounds) {
   z.kmin_bits = 0x7f800000u;
   *S = z;
 }
+cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t stream) {
+  init_state_kernel<<<1, 1, 0, stream>>>(st, max_rounds);
+  return cudaGetLastError();
+}
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {
   init_state_kernel<<<1, 1, 0, stream>>>(a.st, max_rounds);
   cudaError_t e = launch_fill(a.tt, (long long)a.nsrc * a.g.vol, std::numeric_limits<float>::infinity(), stream);
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
-  e = launch_fill(reinterpret_cast<float*>(a.key), (long long)((total + 3) / 4 * 4), std::numeric_limits<float>::infinity(), stream);
+  // keys: exact-length scalar fill (group slices are neither 16-byte aligned nor padded)
+  fill_u32_kernel<<<(unsigned)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(a.key, (long long)total, 0x7f800000u);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   init_sources_kernel<<<a.nsrc, 32, 0, stream>>>(a);
   return cudaGetLastError();

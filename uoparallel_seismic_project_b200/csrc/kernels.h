@@ -72,5 +72,6 @@ cudaError_t launch_pad_box(const float* dense, float* padded, BoxGeom g, cudaStr
 cudaError_t launch_unpad_box(const float* padded, float* dense, BoxGeom g, cudaStream_t stream);
 // tt := INF everywhere, 0 at each start; state, flags and the first work list reset.
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream);
+cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t stream);
 
 }  // namespace sweeptt

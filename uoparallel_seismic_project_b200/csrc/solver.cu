@@ -30,6 +30,8 @@
 
 using namespace sweeptt;
 
+static constexpr int MAX_GROUPS = 8;
+
 // ---------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------
@@ -164,6 +166,21 @@ struct sweeptt_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
 
+  // Source groups (graph loop only): the sources are split into G groups that run as G
+  // independent WHILE graphs on G streams over disjoint slices of the work lists / keys / boxes.
+  // One group's relaxation CTAs fill the SMs that another group's round has already drained, so
+  // the per-round tail (work-list length not a multiple of the SM count) is hidden.
+  struct Group {
+    int s0 = 0, ns = 0;
+    cudaStream_t stream = nullptr;  // null: the context's own stream
+    cudaEvent_t done = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    CUtensorMap tm_tt{};
+  };
+  std::vector<Group> groups;
+  bool groups_valid = false;
+  cudaEvent_t ev_fork = nullptr;
+
   std::vector<cudaEvent_t> prof_events;
   bool allow_outside_sources = false;  // slab contexts: the start may lie in another slab
   int force_window_axis = -1;          // slab contexts: all slabs must share one axis order
@@ -178,6 +195,11 @@ static void invalidate_graph(sweeptt_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   c->graph_exec = nullptr;
   c->graph_valid = false;
+  for (auto& g : c->groups) {
+    if (g.graph) cudaGraphExecDestroy(g.graph);
+    g.graph = nullptr;
+  }
+  c->groups_valid = false;
 }
 
 static int dev_alloc(sweeptt_ctx* c, void** p, size_t bytes) {
@@ -223,8 +245,9 @@ extern "C" sweeptt_ctx* sweeptt_create(const sweeptt_opts* opts) {
   c->own_stream = true;
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
        cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState)) == cudaSuccess &&
-       cudaMallocHost(&c->h_state, sizeof(SolveState)) == cudaSuccess &&
+  ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
+       cudaMallocHost(&c->h_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
+       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
        cudaMalloc(&c->d_viol, sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) {
     fail("context setup failed on device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
@@ -244,6 +267,11 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
     if (it != g_const_owner.end() && it->second == c) { g_const_owner.erase(it); g_const_sig.erase(c->device); }
   }
   invalidate_graph(c);
+  for (auto& g : c->groups) {
+    if (g.stream) cudaStreamDestroy(g.stream);
+    if (g.done) cudaEventDestroy(g.done);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
   cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
@@ -281,6 +309,7 @@ static int ensure_stage(sweeptt_ctx* c, size_t floats) {
 
 static int build_tile_pulls(sweeptt_ctx* c);
 static int build_maps(sweeptt_ctx* c);
+static int encode_tt_map(sweeptt_ctx* c, float* base, int nboxes, CUtensorMap* out);
 static int choose_kernel(sweeptt_ctx* c);
 
 extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, int ny, int nz) {
@@ -568,18 +597,25 @@ static int build_maps(sweeptt_ctx* c) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(slowness) failed: %d", (int)r);
   }
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)g.px, (cuuint64_t)std::max(1, c->tt_cap)};
-    cuuint64_t strides[3] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.sx * 4, (cuuint64_t)g.vol * 4};
-    cuuint32_t box[4] = {(cuuint32_t)szd, (cuuint32_t)syd, (cuuint32_t)sxd, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&c->tm_tt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->d_tt, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(travel times) failed: %d", (int)r);
-  }
+  if (!encode_tt_map(c, c->d_tt, std::max(1, c->tt_cap), &c->tm_tt)) return 0;
   c->maps_valid = true;
   invalidate_graph(c);
+  return 1;
+}
+
+static int encode_tt_map(sweeptt_ctx* c, float* base, int nboxes, CUtensorMap* out) {
+  auto enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from this driver");
+  const BoxGeom& g = c->g;
+  int sxd, syd, szd;
+  tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
+  cuuint64_t dims[4] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)g.px, (cuuint64_t)nboxes};
+  cuuint64_t strides[3] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.sx * 4, (cuuint64_t)g.vol * 4};
+  cuuint32_t box[4] = {(cuuint32_t)szd, (cuuint32_t)syd, (cuuint32_t)sxd, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(travel times) failed: %d", (int)r);
   return 1;
 }
 
@@ -698,9 +734,10 @@ static int read_state(sweeptt_ctx* c) {
 
 // CUDA graph: WHILE(cond) { relax; compact -> sets cond }  -- the whole convergence loop is
 // one graph launch; the host is not consulted between rounds.
-static int build_graph(sweeptt_ctx* c) {
-  if (c->graph_valid) return 1;
-  invalidate_graph(c);
+static int encode_tt_map(sweeptt_ctx* c, float* base, int nboxes, CUtensorMap* out);
+
+static int build_while_graph(sweeptt_ctx* c, const RelaxArgs& a, const CUtensorMap& tm_tt, cudaStream_t stream,
+                             cudaGraphExec_t* exec) {
   cudaGraph_t graph = nullptr;
   CK(cudaGraphCreate(&graph, 0));
   cudaGraphConditionalHandle handle;
@@ -714,17 +751,76 @@ static int build_graph(sweeptt_ctx* c) {
   e = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
   if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail("cudaGraphAddNode(conditional): %s", cudaGetErrorString(e)); }
   cudaGraph_t body = np.conditional.phGraph_out[0];
-  e = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+  e = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
   if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail("cudaStreamBeginCaptureToGraph: %s", cudaGetErrorString(e)); }
-  const RelaxArgs a = make_args(c);
-  int ok = enqueue_round(c, a, (unsigned long long)handle);
+  int ok = 1;
+  if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
+    ok = launch_relax_tiled(c->tl, c->tm_slow, tm_tt, a, stream) == cudaSuccess &&
+         launch_compact(a, (unsigned long long)handle, stream) == cudaSuccess;
+  } else {
+    ok = launch_relax_simple(a, c->d_star, c->nstar, (unsigned long long)c->pulls_per_round * a.nsrc, stream) == cudaSuccess &&
+         launch_advance_simple(a.st, (unsigned long long)handle, stream) == cudaSuccess;
+  }
   cudaGraph_t dummy = nullptr;
-  e = cudaStreamEndCapture(c->stream, &dummy);
-  if (!ok || e != cudaSuccess) { cudaGraphDestroy(graph); return ok ? fail("cudaStreamEndCapture: %s", cudaGetErrorString(e)) : 0; }
-  e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+  e = cudaStreamEndCapture(stream, &dummy);
+  if (!ok || e != cudaSuccess) { cudaGraphDestroy(graph); return fail("capturing the relaxation loop failed: %s", cudaGetErrorString(e)); }
+  e = cudaGraphInstantiate(exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (e != cudaSuccess) { c->graph_exec = nullptr; return fail("cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { *exec = nullptr; return fail("cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  return 1;
+}
+
+// CUDA graph: WHILE(cond) { relax; compact -> sets cond }  -- the whole convergence loop is
+// one graph launch; the host is not consulted between rounds.
+static int build_graph(sweeptt_ctx* c) {
+  if (c->graph_valid) return 1;
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr;
+  if (!build_while_graph(c, make_args(c), c->tm_tt, c->stream, &c->graph_exec)) return 0;
   c->graph_valid = true;
+  return 1;
+}
+
+// slice of the context that group g works on
+static RelaxArgs group_args(sweeptt_ctx* c, int g) {
+  RelaxArgs a = make_args(c);
+  const sweeptt_ctx::Group& G = c->groups[g];
+  const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
+  a.tt = c->d_tt + (size_t)G.s0 * c->g.vol;
+  a.nsrc = G.ns;
+  a.src_xyz = c->d_src + 3 * G.s0;
+  a.st = c->d_state + 1 + g;
+  a.cap = (unsigned)(ntiles * G.ns);
+  a.worklist = c->d_worklist + 2 * ntiles * G.s0;  // each group owns 2*cap consecutive entries
+  a.key = c->d_key + ntiles * G.s0;
+  return a;
+}
+
+static int build_groups(sweeptt_ctx* c, int want) {
+  if (c->groups_valid && (int)c->groups.size() == want) return 1;
+  for (auto& g : c->groups)
+    if (g.graph) { cudaGraphExecDestroy(g.graph); g.graph = nullptr; }
+  while ((int)c->groups.size() > want) {
+    auto& g = c->groups.back();
+    if (g.stream) cudaStreamDestroy(g.stream);
+    if (g.done) cudaEventDestroy(g.done);
+    c->groups.pop_back();
+  }
+  while ((int)c->groups.size() < want) {
+    sweeptt_ctx::Group g;
+    if (!c->groups.empty()) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    c->groups.push_back(g);
+  }
+  for (int g = 0; g < want; ++g) {
+    auto& G = c->groups[g];
+    G.s0 = (int)((long long)c->nsrc * g / want);
+    G.ns = (int)((long long)c->nsrc * (g + 1) / want) - G.s0;
+    if (c->kernel_used == SWEEPTT_KERNEL_TILED && !encode_tt_map(c, c->d_tt + (size_t)G.s0 * c->g.vol, G.ns, &G.tm_tt)) return 0;
+    cudaStream_t st = G.stream ? G.stream : c->stream;
+    if (!build_while_graph(c, group_args(c, g), G.tm_tt, st, &G.graph)) return 0;
+  }
+  c->groups_valid = true;
   return 1;
 }
 
@@ -820,9 +916,74 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
   return 1;
 }
 
+// G concurrent source groups, each its own device-resident WHILE graph (see sweeptt_ctx::Group)
+static int run_groups(sweeptt_ctx* c, int want, sweeptt_stats* stats) {
+  if (!build_groups(c, want)) return 0;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  for (int g = 0; g < want; ++g) {
+    auto& G = c->groups[g];
+    cudaStream_t st = G.stream ? G.stream : c->stream;
+    if (G.stream) CK(cudaStreamWaitEvent(G.stream, c->ev_fork, 0));
+    CK(launch_reset(group_args(c, g), c->opts.max_rounds, st));
+    CK(cudaGraphLaunch(G.graph, st));
+    if (G.stream) {
+      CK(cudaEventRecord(G.done, G.stream));
+    }
+  }
+  for (int g = 0; g < want; ++g)
+    if (c->groups[g].stream) CK(cudaStreamWaitEvent(c->stream, c->groups[g].done, 0));
+  // the single-group view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
+  {
+    RelaxArgs whole = make_args(c);
+    CK(launch_reset_state_only(whole.st, c->opts.max_rounds, c->stream));
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState) * (1 + want), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  int pending = 0;
+  if (stats) {
+    std::memset(stats, 0, sizeof *stats);
+    stats->struct_size = sizeof *stats;
+    stats->kernel_used = c->kernel_used;
+    stats->devices_used = 1;
+    stats->solve_ms = ms;
+  }
+  for (int g = 0; g < want; ++g) {
+    const SolveState& h = c->h_state[1 + g];
+    pending |= (c->kernel_used == SWEEPTT_KERNEL_TILED) ? (h.count[h.parity] != 0) : (h.last_changed_round == h.round);
+    if (stats) {
+      stats->rounds = std::max(stats->rounds, h.round);
+      stats->kernel_launches += (c->kernel_used == SWEEPTT_KERNEL_TILED ? 3LL : 2LL) * h.round + 4;
+      stats->relax_launches += h.round;
+      stats->tile_visits += (long long)h.tile_visits;
+      stats->relaxations += (long long)h.pulls;
+      stats->units_run += (long long)h.units_run;
+      stats->units_changed += (long long)h.units_changed;
+    }
+  }
+  if (pending && c->opts.max_rounds > 0) return fail("not converged after max_rounds = %d rounds", c->opts.max_rounds);
+  return 1;
+}
+
 extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
   if (!ready(c)) return 0;
   if (stats) { std::memset(stats, 0, sizeof *stats); }
+  {
+    int loop = c->opts.loop;
+    if (const char* env = getenv("SWEEPTT_LOOP")) {
+      if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
+      if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
+    }
+    int want = 2;
+    if (const char* env = getenv("SWEEPTT_GROUPS")) want = atoi(env);
+    want = std::max(1, std::min({want, c->nsrc, MAX_GROUPS}));
+    if ((loop == SWEEPTT_LOOP_AUTO || loop == SWEEPTT_LOOP_GRAPH) && !c->opts.profile_kernels && want > 1)
+      return run_groups(c, want, stats);
+  }
   CK(cudaEventRecord(c->ev0, c->stream));
   CK(launch_reset(make_args(c), c->opts.max_rounds, c->stream));
   int changed = 0;
