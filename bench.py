@@ -180,6 +180,15 @@ def run_reference(args):
     return 0
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -322,7 +331,7 @@ def run_ours(args):
             "hbm": {"achieved": tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9
                     if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
                     "note": "12 B per node per tile visit; the path is ~50x away from the HBM roof (SURVEY.md 8d)"},
-            "traffic": None,
+            "traffic": _ncu_traffic(),
         },
     }
     if not args.no_cpu_baseline and world == 1:
