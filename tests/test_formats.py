@@ -24,6 +24,20 @@ def test_vbox_store_bytes_match_oracle_and_vconvert(tmp_path):
         assert (tmp_path / "ref.vbox").read_bytes() == (tmp_path / "ours.vbox").read_bytes()
 
 
+def test_vconvert_tool_matches_reference_tool(tmp_path):
+    v = W.heterogeneous_field((5, 6, 7), seed=9)
+    W.write_text_a(tmp_path / "v.txt", v)
+    ours = P.lib_path().parent / "vconvert"
+    r = subprocess.run([str(ours), str(tmp_path / "v.txt"), str(tmp_path / "ours.vbox")], capture_output=True, text=True)
+    assert r.returncode == 0 and "writing new velocity model" in r.stdout
+    got, origin, dims = P.vbox_load(tmp_path / "ours.vbox")
+    assert origin == (1, 1, 1) and np.array_equal(got, v)
+    vc = oracle.vconvert_path()
+    if vc is not None:
+        subprocess.run([str(vc), str(tmp_path / "v.txt"), str(tmp_path / "ref.vbox")], check=True, capture_output=True)
+        assert (tmp_path / "ref.vbox").read_bytes() == (tmp_path / "ours.vbox").read_bytes()
+
+
 def test_vbox_checksum_is_the_sign_extended_sum(tmp_path):
     v = np.array([[[-1.5, 2.0, -3.25]]], np.float32)
     P.vbox_store(tmp_path / "a.vbox", v)

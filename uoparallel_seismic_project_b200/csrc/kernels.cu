@@ -227,6 +227,10 @@ __device__ __forceinline__ void relax_column(const float (&W)[WIN], const float 
   }
 }
 
+#ifndef SWEEPTT_SCHED_FENCE
+#define SWEEPTT_SCHED_FENCE() ((void)0)  // measured: forcing the window loads above the FP block with __syncwarp() is SLOWER (21.7 vs 20.0 ms)
+#endif
+
 // all columns [cbeg,cend) share the compile-time pattern KMASK: branch-free unrolled blocks,
 // the next column's window is fetched (ping-pong registers) while the current one computes
 template <uint32_t KMASK>
@@ -251,8 +255,11 @@ __device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const 
     load_window<GM>(sv + b0 + soffB, st + b0 + soffB, Wb, Tb);
     soffA = c_cols[c + 2].soff;
     soffB = c_cols[c + 3].soff;
+    SWEEPTT_SCHED_FENCE();  // keeps the window loads ABOVE the FP block they overlap with (ptxas otherwise
+                            // sinks each LDS next to its first use, which exposes the smem latency)
     relax_column<KMASK>(Wa, Ta, hi, vn, vnE, vnO, nz2, acc);
     load_window<GM>(sv + b0 + soffA, st + b0 + soffA, Wa, Ta);
+    SWEEPTT_SCHED_FENCE();
     relax_column<KMASK>(Wb, Tb, hi + NK, vn, vnE, vnO, nz2, acc);
     hi += 2 * NK;
   }
@@ -370,48 +377,71 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
 
     // whole-warp skip when this warp's nodes are all outside the grid
     const bool warp_live = (x0 + ((warp >> 2) << 2) < a.g.nx) && (z0 + zc * KZ < a.g.nz);
-    int changed = 0;
+    const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
+    const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
+    float vn[KZ], told[KZ], acc[KZ];
     if (warp_live) {
-      float vn[KZ], told[KZ], acc[KZ];
-      {
-        const float4 v0 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO);
-        const float4 v1 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4);
-        const float4 t0 = *reinterpret_cast<const float4*>(st + b0 + ZHALO);
-        const float4 t1 = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4);
-        vn[0] = v0.x; vn[1] = v0.y; vn[2] = v0.z; vn[3] = v0.w;
-        vn[4] = v1.x; vn[5] = v1.y; vn[6] = v1.z; vn[7] = v1.w;
-        told[0] = t0.x; told[1] = t0.y; told[2] = t0.z; told[3] = t0.w;
-        told[4] = t1.x; told[5] = t1.y; told[6] = t1.z; told[7] = t1.w;
-      }
+      const float4 v0 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO);
+      const float4 v1 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4);
+      const float4 t0 = *reinterpret_cast<const float4*>(st + b0 + ZHALO);
+      const float4 t1 = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4);
+      vn[0] = v0.x; vn[1] = v0.y; vn[2] = v0.z; vn[3] = v0.w;
+      vn[4] = v1.x; vn[5] = v1.y; vn[6] = v1.z; vn[7] = v1.w;
+      told[0] = t0.x; told[1] = t0.y; told[2] = t0.z; told[3] = t0.w;
+      told[4] = t1.x; told[5] = t1.y; told[6] = t1.z; told[7] = t1.w;
 #pragma unroll
       for (int k = 0; k < KZ; ++k) acc[k] = told[k];
+    }
 
-      columns_phase(STAR{}, sv, st, b0, a, vn, acc);
-
-      // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
-      //      serial_new/...c:219-221 with :160) and duplicates ----
-      const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
-      const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
-      for (int e = 0; e < a.nextra; ++e) {
-        const ExtraDev ex = c_extra[e];
-        const float* pv = sv + b0 + ZHALO + ex.soff;
-        const float* pt = st + b0 + ZHALO + ex.soff;
+    // In-tile iterations (block Gauss-Seidel): while the tile's own nodes keep changing, publish the
+    // new values to the staged box and relax again against the same halo -- information then
+    // crosses the tile in one visit instead of one hop per round.  Every pass is a set of valid
+    // relaxations, so the fixed point is unchanged.
+    int reps = 0;
+    int last_pass_changed = 0;
+    for (;;) {
+      int pass_changed = 0;
+      if (warp_live) {
+        float before[KZ];
 #pragma unroll
-        for (int k = 0; k < KZ; ++k) {
-          const bool bad = ex.guarded && (gx + ex.i == px) && (gy + ex.j == py) && (gz + k + ex.k == pz);
-          const float delay = __fmul_rn(ex.hd, __fadd_rn(vn[k], pv[k]));
-          const float cand = __fadd_rn(delay, pt[k]);
-          if (!bad) acc[k] = fminf(acc[k], cand);
+        for (int k = 0; k < KZ; ++k) before[k] = acc[k];
+        columns_phase(STAR{}, sv, st, b0, a, vn, acc);
+
+        // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
+        //      serial_new/...c:219-221 with :160) and duplicates ----
+        for (int e = 0; e < a.nextra; ++e) {
+          const ExtraDev ex = c_extra[e];
+          const float* pv = sv + b0 + ZHALO + ex.soff;
+          const float* pt = st + b0 + ZHALO + ex.soff;
+#pragma unroll
+          for (int k = 0; k < KZ; ++k) {
+            const bool bad = ex.guarded && (gx + ex.i == px) && (gy + ex.j == py) && (gz + k + ex.k == pz);
+            const float delay = __fmul_rn(ex.hd, __fadd_rn(vn[k], pv[k]));
+            const float cand = __fadd_rn(delay, pt[k]);
+            if (!bad) acc[k] = fminf(acc[k], cand);
+          }
         }
-      }
-
-      // the start point itself is never relaxed (serial_new/...c:219-221)
-      if (gx == px && gy == py) {
+        // the start point itself is never relaxed (serial_new/...c:219-221)
+        if (gx == px && gy == py) {
 #pragma unroll
-        for (int k = 0; k < KZ; ++k)
-          if (gz + k == pz) acc[k] = told[k];
+          for (int k = 0; k < KZ; ++k)
+            if (gz + k == pz) acc[k] = told[k];
+        }
+#pragma unroll
+        for (int k = 0; k < KZ; ++k) pass_changed |= (acc[k] < before[k]);
       }
+      ++reps;
+      last_pass_changed = __syncthreads_or(pass_changed);  // also: every thread is done reading the staged box
+      if (!last_pass_changed || reps >= a.max_inner) break;
+      if (pass_changed) {
+        *reinterpret_cast<float4*>(st + b0 + ZHALO) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(st + b0 + ZHALO + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      __syncthreads();
+    }
 
+    int changed = 0;
+    if (warp_live) {
       float tmin = CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < KZ; ++k) {
@@ -427,7 +457,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       // warp-level reduction of "what changed": travel times are >= 0, so float order == uint order
       const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(tmin));
       if (lane == 0) {
-        atomicAdd(&S->units_run, 1ull);
+        atomicAdd(&S->units_run, (unsigned long long)reps);
         if (wmin != 0x7f800000u) {
           atomicAdd(&S->units_changed, 1ull);
           atomicMin(&s_tmin, wmin);
@@ -440,18 +470,20 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int any = __syncthreads_or(changed);
     if (any && tid < 27) {
       // a changed node reaches R <= 7 cells: every x/y neighbour tile (8 wide) is affected, the
-      // z neighbours (32 long) only when the first / last z chunk changed
+      // z neighbours (32 long) only when the first / last z chunk changed; the tile itself only
+      // needs another visit if its last in-tile pass still changed something
       const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
       const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
       const unsigned zm = s_zmask;
-      const bool reach = (dz == 0) || (dz < 0 && (zm & 1u)) || (dz > 0 && (zm & (1u << (TZ / KZ - 1))));
+      bool reach = (dz == 0) || (dz < 0 && (zm & 1u)) || (dz > 0 && (zm & (1u << (TZ / KZ - 1))));
+      if (tid == 13 && !last_pass_changed) reach = false;  // self
       if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
         atomicMin(&a.key[(size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz], s_tmin);
     }
     if (tid == 32) {
       const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
       atomicAdd(&S->tile_visits, 1ull);
-      atomicAdd(&S->pulls, a.tile_pulls[tpos]);
+      atomicAdd(&S->pulls, a.tile_pulls[tpos] * (unsigned long long)reps);
       if (any) atomicMax(&S->last_changed_round, round + 1);
     }
   }

@@ -41,6 +41,7 @@ struct RelaxArgs {
   float bucket;                // only tiles with key <= (smallest key) + bucket run in a round; <0 = all
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
+  int max_inner;               // in-tile relaxation passes per visit (>= 1)
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
