@@ -7,7 +7,11 @@ namespace sweeptt {
 // ---- tile shape of the tiled kernel -------------------------------------------------
 // Interior tile TX x TY x TZ nodes; each thread owns KZ consecutive z nodes of one (x,y)
 // column (register window along the fastest axis).  256 threads per CTA.
-constexpr int TX = 8, TY = 8, TZ = 32, KZ = 8;
+#ifndef SWEEPTT_KZ
+#define SWEEPTT_KZ 8
+#endif
+constexpr int TX = 8, TY = 8, TZ = 32, KZ = SWEEPTT_KZ;
+constexpr int ZCHUNKS = TZ / KZ;
 constexpr int ZHALO = 8;                 // z halo staged on both sides (16-byte aligned)
 constexpr int SZD = TZ + 2 * ZHALO + 4;  // smem/TMA row length: 52 floats; 52/4 = 13 is odd,
                                          // which makes the quarter-warp LDS.128 conflict-free

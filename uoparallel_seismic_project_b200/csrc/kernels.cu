@@ -330,8 +330,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   const int lane = tid & 31, warp = tid >> 5;
   // warp -> (x half, z chunk); lane -> (x within half, y): a quarter-warp shares x and zc and
   // spans 8 consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
-  const int zc = warp & 3;
-  const int x = ((warp >> 2) << 2) | (lane >> 3);
+  const int zc = warp % ZCHUNKS;
+  const int x = ((warp / ZCHUNKS) << 2) | (lane >> 3);
   const int y = lane & 7;
 
   if (tid == 0) {
@@ -376,19 +376,18 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     mbar_wait(&bar, it & 1);
 
     // whole-warp skip when this warp's nodes are all outside the grid
-    const bool warp_live = (x0 + ((warp >> 2) << 2) < a.g.nx) && (z0 + zc * KZ < a.g.nz);
+    const bool warp_live = (x0 + ((warp / ZCHUNKS) << 2) < a.g.nx) && (z0 + zc * KZ < a.g.nz);
     const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
     float vn[KZ], told[KZ], acc[KZ];
     if (warp_live) {
-      const float4 v0 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO);
-      const float4 v1 = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4);
-      const float4 t0 = *reinterpret_cast<const float4*>(st + b0 + ZHALO);
-      const float4 t1 = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4);
-      vn[0] = v0.x; vn[1] = v0.y; vn[2] = v0.z; vn[3] = v0.w;
-      vn[4] = v1.x; vn[5] = v1.y; vn[6] = v1.z; vn[7] = v1.w;
-      told[0] = t0.x; told[1] = t0.y; told[2] = t0.z; told[3] = t0.w;
-      told[4] = t1.x; told[5] = t1.y; told[6] = t1.z; told[7] = t1.w;
+#pragma unroll
+      for (int q = 0; q < KZ / 4; ++q) {
+        const float4 vv = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4 * q);
+        const float4 tv = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4 * q);
+        vn[4 * q] = vv.x; vn[4 * q + 1] = vv.y; vn[4 * q + 2] = vv.z; vn[4 * q + 3] = vv.w;
+        told[4 * q] = tv.x; told[4 * q + 1] = tv.y; told[4 * q + 2] = tv.z; told[4 * q + 3] = tv.w;
+      }
 #pragma unroll
       for (int k = 0; k < KZ; ++k) acc[k] = told[k];
     }
@@ -434,8 +433,9 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       last_pass_changed = __syncthreads_or(pass_changed);  // also: every thread is done reading the staged box
       if (!last_pass_changed || reps >= a.max_inner) break;
       if (pass_changed) {
-        *reinterpret_cast<float4*>(st + b0 + ZHALO) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(st + b0 + ZHALO + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+        for (int q = 0; q < KZ / 4; ++q)
+          *reinterpret_cast<float4*>(st + b0 + ZHALO + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
       }
       __syncthreads();
     }
@@ -451,8 +451,9 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       }
       if (changed) {
         float* out = a.tt + (size_t)s * a.g.vol + ((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ);
-        *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+        for (int q = 0; q < KZ / 4; ++q)
+          *reinterpret_cast<float4*>(out + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
       }
       // warp-level reduction of "what changed": travel times are >= 0, so float order == uint order
       const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(tmin));
