@@ -116,6 +116,7 @@ struct TileDims {
   // second box starts on a 1024-byte boundary (TMA destinations must be 128-byte aligned)
   static constexpr int BOX_STRIDE = (BOX_FLOATS * 4 + 1023) / 1024 * 1024 / 4;
   static constexpr size_t SMEM = sizeof(float) * (BOX_STRIDE + BOX_FLOATS) + 1024;  // + alignment slack
+  static constexpr size_t SMEM_SPLIT = sizeof(float) * (2 * BOX_STRIDE + TILE_THREADS * KZ) + 1024;
 };
 
 // ---- column phase -------------------------------------------------------------------------
@@ -265,9 +266,32 @@ __device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const 
   }
 }
 
-template <uint32_t... M>
+// SPLIT = 2: two thread groups own the same nodes and each runs HALF of every pattern's columns
+// (16 warps per SM at the same shared-memory footprint; results min-combined through smem).
+// Register budget is 128 per thread there, so the windows are single-buffered and latency is
+// hidden by the extra warps instead of the ping-pong.
+template <uint32_t KMASK>
+__device__ __forceinline__ void run_pattern_half(const float* __restrict__ sv, const float* __restrict__ st, int b0,
+                                                 int pb, int pe, int half, const float (&vn)[KZ],
+                                                 const u64 (&vnE)[KZ / 2], const u64 (&vnO)[KZ / 2 - 1], u64 nz2,
+                                                 float (&acc)[KZ]) {
+  constexpr uint32_t GM = granules_of(KMASK);
+  constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
+  if (pb >= pe) return;
+  const int mid = pb + (pe - pb) / 2;
+  const int cb = half ? mid : pb, ce = half ? pe : mid;
+  const int hi0 = c_cols[pb].hd_begin;
+  float W[WIN], T[WIN];
+  for (int c = cb; c < ce; ++c) {
+    const int soff = c_cols[c].soff;
+    load_window<GM>(sv + b0 + soff, st + b0 + soff, W, T);
+    relax_column<KMASK>(W, T, hi0 + (c - pb) * NK, vn, vnE, vnO, nz2, acc);
+  }
+}
+
+template <int SPLIT, uint32_t... M>
 __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
-                                              const float* __restrict__ st, int b0, const RelaxArgs& a,
+                                              const float* __restrict__ st, int b0, const RelaxArgs& a, int half,
                                               const float (&vn)[KZ], float (&acc)[KZ]) {
   if constexpr (sizeof...(M) == 0) {
     // generic: runtime masks (any star that fits the halo)
@@ -308,12 +332,16 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
     for (int j = 0; j < KZ / 2 - 1; ++j) vnO[j] = pack2(vn[2 * j + 1], vn[2 * j + 2]);
     const u64 nz2 = pack2(a.neg_zero, a.neg_zero);
     int p = 0;
-    ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, vnE, vnO, nz2, acc), ++p), ...);
+    if constexpr (SPLIT == 1) {
+      ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, vnE, vnO, nz2, acc), ++p), ...);
+    } else {
+      ((run_pattern_half<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], half, vn, vnE, vnO, nz2, acc), ++p), ...);
+    }
   }
 }
 
-template <int RXY, typename STAR>
-__global__ void __launch_bounds__(TILE_THREADS, (RXY == 7) ? 1 : 2)
+template <int RXY, typename STAR, int SPLIT = 1>
+__global__ void __launch_bounds__(TILE_THREADS * SPLIT, (RXY == 7) ? 1 : 2)
 relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
             const __grid_constant__ RelaxArgs a) {
   using D = TileDims<RXY>;
@@ -321,13 +349,16 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   // 1024-byte aligned carve-up: [slowness box][travel-time box]
   float* sv = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   float* st = sv + D::BOX_STRIDE;
+  float* s_comb = st + D::BOX_STRIDE;  // SPLIT == 2: [k][thread] accumulators of the second thread group
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_tile;
   __shared__ unsigned s_tmin;   // float bits of the smallest travel time this tile lowered
   __shared__ unsigned s_zmask;  // which z chunks changed
 
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int half = (SPLIT == 1) ? 0 : tid / TILE_THREADS;  // which half of the star's columns this thread runs
+  const int t = tid - half * TILE_THREADS;
+  const int lane = t & 31, warp = t >> 5;
   // warp -> (x half, z chunk); lane -> (x within half, y): a quarter-warp shares x and zc and
   // spans 8 consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
   const int zc = warp % ZCHUNKS;
@@ -389,7 +420,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         told[4 * q] = tv.x; told[4 * q + 1] = tv.y; told[4 * q + 2] = tv.z; told[4 * q + 3] = tv.w;
       }
 #pragma unroll
-      for (int k = 0; k < KZ; ++k) acc[k] = told[k];
+      for (int k = 0; k < KZ; ++k) acc[k] = half ? CUDART_INF_F : told[k];
     }
 
     // In-tile iterations (block Gauss-Seidel): while the tile's own nodes keep changing, publish the
@@ -400,15 +431,15 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     int last_pass_changed = 0;
     for (;;) {
       int pass_changed = 0;
+      float beforeq[KZ];
       if (warp_live) {
-        float before[KZ];
 #pragma unroll
-        for (int k = 0; k < KZ; ++k) before[k] = acc[k];
-        columns_phase(STAR{}, sv, st, b0, a, vn, acc);
+        for (int k = 0; k < KZ; ++k) beforeq[k] = acc[k];
+        columns_phase<SPLIT>(STAR{}, sv, st, b0, a, half, vn, acc);
 
         // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
         //      serial_new/...c:219-221 with :160) and duplicates ----
-        for (int e = 0; e < a.nextra; ++e) {
+        for (int e = 0; e < (half ? 0 : a.nextra); ++e) {
           const ExtraDev ex = c_extra[e];
           const float* pv = sv + b0 + ZHALO + ex.soff;
           const float* pt = st + b0 + ZHALO + ex.soff;
@@ -420,6 +451,19 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (!bad) acc[k] = fminf(acc[k], cand);
           }
         }
+        if constexpr (SPLIT == 2) {
+          if (half) {
+#pragma unroll
+            for (int k = 0; k < KZ; ++k) s_comb[k * TILE_THREADS + t] = acc[k];
+          }
+        }
+      }
+      if constexpr (SPLIT == 2) __syncthreads();
+      if (warp_live && half == 0) {
+        if constexpr (SPLIT == 2) {
+#pragma unroll
+          for (int k = 0; k < KZ; ++k) acc[k] = fminf(acc[k], s_comb[k * TILE_THREADS + t]);
+        }
         // the start point itself is never relaxed (serial_new/...c:219-221)
         if (gx == px && gy == py) {
 #pragma unroll
@@ -427,12 +471,12 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (gz + k == pz) acc[k] = told[k];
         }
 #pragma unroll
-        for (int k = 0; k < KZ; ++k) pass_changed |= (acc[k] < before[k]);
+        for (int k = 0; k < KZ; ++k) pass_changed |= (acc[k] < beforeq[k]);
       }
       ++reps;
       last_pass_changed = __syncthreads_or(pass_changed);  // also: every thread is done reading the staged box
       if (!last_pass_changed || reps >= a.max_inner) break;
-      if (pass_changed) {
+      if (pass_changed && half == 0) {
 #pragma unroll
         for (int q = 0; q < KZ / 4; ++q)
           *reinterpret_cast<float4*>(st + b0 + ZHALO + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
@@ -441,7 +485,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     }
 
     int changed = 0;
-    if (warp_live) {
+    if (warp_live && half == 0) {
       float tmin = CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < KZ; ++k) {
@@ -772,26 +816,46 @@ int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed)
   return 0;
 }
 
-template <int RXY, typename STAR>
+template <int RXY, typename STAR, int SPLIT = 1>
 static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   using D = TileDims<RXY>;
-  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
+  const size_t smem = SPLIT == 1 ? D::SMEM : D::SMEM_SPLIT;
+  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR>, TILE_THREADS, D::SMEM);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR, SPLIT>, TILE_THREADS * SPLIT, smem);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   out->rxy = RXY;
   out->grid = per_sm * sms;
-  out->smem_bytes = D::SMEM;
+  out->smem_bytes = smem;
+  out->split = SPLIT;
   return cudaSuccess;
 }
-cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
+template <int R, typename STAR>
+static cudaError_t prepare_any(int split, int device, TiledLaunch* out) {
+  if constexpr (R == 7) {  // the split variant only exists where one CTA per SM is the limit
+    if (split == 2) return prepare_variant<R, STAR, 2>(device, out);
+  }
+  return prepare_variant<R, STAR, 1>(device, out);
+}
+template <int R, typename STAR>
+static void launch_any(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt, const RelaxArgs& a,
+                       cudaStream_t stream) {
+  if constexpr (R == 7) {
+    if (tl.split == 2) {
+      relax_tiled<R, STAR, 2><<<tl.grid, 2 * TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+      return;
+    }
+  }
+  relax_tiled<R, STAR, 1><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+}
+cudaError_t tiled_prepare(int rxy, int stock_id, int split, int device, TiledLaunch* out) {
   out->stock_id = stock_id;
 #define SWEEPTT_STOCK_STAR(id, name, r, ...) \
-  if (stock_id == id) return prepare_variant<r, Star_##name>(device, out);
+  if (stock_id == id) return prepare_any<r, Star_##name>(split, device, out);
 #include "stock_stars.inc"
 #undef SWEEPTT_STOCK_STAR
   switch (rxy) {
@@ -804,10 +868,10 @@ cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
                                const RelaxArgs& a, cudaStream_t stream) {
-#define SWEEPTT_STOCK_STAR(id, name, r, ...)                                                                  \
-  if (tl.stock_id == id) {                                                                                    \
-    relax_tiled<r, Star_##name><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);         \
-    return cudaGetLastError();                                                                                \
+#define SWEEPTT_STOCK_STAR(id, name, r, ...)                   \
+  if (tl.stock_id == id) {                                     \
+    launch_any<r, Star_##name>(tl, tm_slow, tm_tt, a, stream); \
+    return cudaGetLastError();                                 \
   }
 #include "stock_stars.inc"
 #undef SWEEPTT_STOCK_STAR

@@ -10,6 +10,7 @@ namespace sweeptt {
 struct TiledLaunch {
   int rxy;                   // halo template: 2, 4 or 7
   int stock_id;              // 0 = generic runtime-mask kernel, else a stock-star instantiation
+  int split;                 // 1, or 2 = two thread groups share the star's columns (16 warps per SM)
   int grid;                  // persistent CTAs
   size_t smem_bytes;
 };
@@ -19,7 +20,7 @@ int tiled_variant_for_radius(int r);
 // smem row/plane pitches of a variant (host needs them to precompute column offsets).
 void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd);
 // Occupancy-derived persistent grid + opt-in shared memory; returns cudaSuccess or an error.
-cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out);
+cudaError_t tiled_prepare(int rxy, int stock_id, int split, int device, TiledLaunch* out);
 // Stock-star instantiation whose compile-time pattern list equals `masks` (ascending), or 0.
 int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed);
 

@@ -515,7 +515,9 @@ static int choose_kernel(sweeptt_ctx* c) {
     stock = tiled_stock_star_for(masks.data(), (int)masks.size(), rxy);
   const char* force = getenv("SWEEPTT_FORCE_RXY");  // testing: run a small star in a wider halo variant
   if (force && atoi(force) >= rxy) { rxy = tiled_variant_for_radius(atoi(force)); stock = 0; }
-  CK(tiled_prepare(rxy, stock, c->device, &c->tl));
+  int split = 2;  // two thread groups per tile for the R=7 stock kernels (16 warps per SM): +2 % measured
+  if (const char* e = getenv("SWEEPTT_SPLIT")) split = atoi(e) == 2 ? 2 : 1;
+  CK(tiled_prepare(rxy, stock, (stock && rxy == 7) ? split : 1, c->device, &c->tl));
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
   c->consts_rxy = -1;
