@@ -356,13 +356,14 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   __shared__ unsigned s_zmask;  // which z chunks changed
 
   const int tid = threadIdx.x;
-  const int half = (SPLIT == 1) ? 0 : tid / TILE_THREADS;  // which half of the star's columns this thread runs
-  const int t = tid - half * TILE_THREADS;
-  const int lane = t & 31, warp = t >> 5;
-  // warp -> (x half, z chunk); lane -> (x within half, y): a quarter-warp shares x and zc and
-  // spans 8 consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
-  const int zc = warp % ZCHUNKS;
-  const int x = ((warp / ZCHUNKS) << 2) | (lane >> 3);
+  const int lane = tid & 31, wq = tid >> 5;  // wq: warp index in the CTA (0 .. 8*SPLIT-1)
+  // lane -> (x within a 4-wide x half, y): a quarter-warp shares x and z chunk and spans 8
+  // consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
+  // Which (x half, z chunk) unit -- and, with SPLIT, which half of the star -- a warp works on is
+  // decided per tile from the tile's LIVE units (those with nodes inside the grid): the busy warps
+  // are always warps 0..SPLIT*nlive-1, so the four schedulers stay evenly loaded when part of a
+  // tile hangs outside the grid (e.g. nz = 51: the upper z tile has 6 live units -> 12 of 16 warps,
+  // 3 per scheduler, instead of two schedulers idling behind two full ones).
   const int y = lane & 7;
 
   if (tid == 0) {
@@ -377,9 +378,6 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   const unsigned* wl = a.worklist + (size_t)par * a.cap;
   const int round = S->round;
   const int ntiles = a.g.ntx * a.g.nty * a.g.ntz;
-
-  // smem float index of this thread's window start for the (0,0) column
-  const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD + zc * KZ;
 
   for (uint32_t it = 0;; ++it) {
     if (tid == 0) {
@@ -406,8 +404,18 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     }
     mbar_wait(&bar, it & 1);
 
-    // whole-warp skip when this warp's nodes are all outside the grid
-    const bool warp_live = (x0 + ((warp / ZCHUNKS) << 2) < a.g.nx) && (z0 + zc * KZ < a.g.nz);
+    // live units of this tile and this warp's assignment
+    const int nxh = (x0 + 4 < a.g.nx) ? 2 : 1;
+    const int nzc = min(ZCHUNKS, (a.g.nz - z0 + KZ - 1) / KZ);
+    const int nlive = nxh * nzc;
+    const bool warp_live = wq < SPLIT * nlive;
+    const int half = (SPLIT == 1) ? 0 : wq / nlive;  // which half of the star's columns
+    const int li = wq - half * nlive;                // live unit index
+    const int xh = li / nzc, zc = li - xh * nzc;
+    const int t = li * 32 + lane;                    // thread index within the thread group
+    const int x = (xh << 2) | (lane >> 3);
+    // smem float index of this thread's window start for the (0,0) column
+    const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD + zc * KZ;
     const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
     float vn[KZ], told[KZ], acc[KZ];
