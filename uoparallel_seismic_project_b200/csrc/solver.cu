@@ -1282,19 +1282,24 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
     cudaSetDevice(b); if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
   }
 
-  // ---- outer loop: local convergence on every slab, then halo exchange -------------------------
+  // ---- outer loop: K relaxation rounds on every slab concurrently, then halo exchange -----------
+  // (K small: the front crosses slab boundaries while all slabs keep working; waiting for local
+  //  convergence before exchanging would serialise the slabs behind the one that holds the source)
   sweeptt_stats total{};
   total.struct_size = sizeof total;
   const auto t0 = std::chrono::steady_clock::now();
+  const int K = o.rounds_per_poll > 0 ? o.rounds_per_poll : 8;
   int outer = 0;
   for (;; ++outer) {
     std::vector<std::thread> th;
+    std::vector<int> pending(G, 0);
     for (int d = 0; d < G; ++d)
       th.emplace_back([&, d] {
         Slab& sl = slabs[d];
         if (cudaSetDevice(sl.device) != cudaSuccess) { sl.ok = 0; sl.err = "cudaSetDevice failed"; return; }
         int changed = 0;
-        sl.ok = run_rounds(sl.ctx, true, 0, &changed, &sl.st);
+        sl.ok = run_rounds(sl.ctx, false, K, &changed, &sl.st);
+        pending[d] = changed;
         if (!sl.ok) sl.err = g_err;
       });
     for (auto& t : th) t.join();
@@ -1328,10 +1333,11 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
       CK(cudaMemcpyAsync(&f, slabs[d].d_flag, sizeof f, cudaMemcpyDeviceToHost, slabs[d].ctx->stream));
       CK(cudaStreamSynchronize(slabs[d].ctx->stream));
       any |= f;
+      any |= (unsigned)pending[d];
     }
-    if (o.verbose > 0) fprintf(stderr, "[sweeptt] slab exchange %d: %s\n", outer, any ? "halos lowered" : "no change");
-    if (!any) break;  // no halo changed after every slab had converged locally: global fixed point
-    if (o.max_rounds > 0 && outer >= o.max_rounds) { cleanup(); return fail("slabs not converged after %d exchanges", outer); }
+    if (o.verbose > 0) fprintf(stderr, "[sweeptt] slab exchange %d: %s\n", outer, any ? "work pending" : "converged");
+    if (!any) break;  // every slab drained its work list and no halo was lowered: global fixed point
+    if (o.max_rounds > 0 && outer * K >= o.max_rounds) { cleanup(); return fail("slabs not converged after %d rounds", outer * K); }
   }
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
