@@ -184,36 +184,43 @@ __host__ __device__ constexpr int popc_below(uint32_t m, int b) {
 // Node pairs (2j,2j+1) for even window shifts, (2j+1,2j+2) + two scalar ends for odd shifts, so
 // that the window operands are always naturally aligned register pairs.  Candidates of two
 // consecutive offsets are folded with one 3-input min (FMNMX3).
-template <uint32_t KMASK>
-__device__ __forceinline__ void relax_column(const float (&W)[WIN], const float (&T)[WIN], int hi,
-                                             const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
-                                             const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
-  float pend[KZ];
+// candidates of ONE k offset (window shift B = k + ZHALO, compile-time) for the thread's KZ nodes
+template <int B>
+__device__ __forceinline__ void offset_candidates(const float (&W)[WIN], const float (&T)[WIN], float hd,
+                                                  const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                                  const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&cand)[KZ]) {
+  const u64 hd2 = pack2(hd, hd);
+  if constexpr ((B & 1) == 0) {
 #pragma unroll
-  for (int b = 0; b <= 2 * ZHALO; ++b) {  // k = b - ZHALO
-    if (KMASK & (1u << b)) {
-      const float hd = c_col_hd[hi++];
-      const u64 hd2 = pack2(hd, hd);
+    for (int j = 0; j < KZ / 2; ++j) {
+      const u64 sum = add2(vnE[j], pack2(W[2 * j + B], W[2 * j + B + 1]));
+      const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[2 * j + B], T[2 * j + B + 1]));
+      unpack2(c2, cand[2 * j], cand[2 * j + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < KZ / 2 - 1; ++j) {
+      constexpr int dummy = 0; (void)dummy;
+      const int k = 2 * j + 1;
+      const u64 sum = add2(vnO[j], pack2(W[k + B], W[k + B + 1]));
+      const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[k + B], T[k + B + 1]));
+      unpack2(c2, cand[k], cand[k + 1]);
+    }
+    cand[0] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[0], W[B])), T[B]);
+    cand[KZ - 1] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[KZ - 1], W[KZ - 1 + B])), T[KZ - 1 + B]);
+  }
+}
+
+template <uint32_t KMASK, int B>
+__device__ __forceinline__ void relax_offsets_from(const float (&W)[WIN], const float (&T)[WIN], int& hi,
+                                                   const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                                   const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ],
+                                                   float (&pend)[KZ]) {
+  if constexpr (B <= 2 * ZHALO) {
+    if constexpr ((KMASK >> B) & 1u) {
       float cand[KZ];
-      if ((b & 1) == 0) {
-#pragma unroll
-        for (int j = 0; j < KZ / 2; ++j) {
-          const u64 sum = add2(vnE[j], pack2(W[2 * j + b], W[2 * j + b + 1]));
-          const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[2 * j + b], T[2 * j + b + 1]));
-          unpack2(c2, cand[2 * j], cand[2 * j + 1]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < KZ / 2 - 1; ++j) {
-          const int k = 2 * j + 1;
-          const u64 sum = add2(vnO[j], pack2(W[k + b], W[k + b + 1]));
-          const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[k + b], T[k + b + 1]));
-          unpack2(c2, cand[k], cand[k + 1]);
-        }
-        cand[0] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[0], W[b])), T[b]);
-        cand[KZ - 1] = __fadd_rn(__fmul_rn(hd, __fadd_rn(vn[KZ - 1], W[KZ - 1 + b])), T[KZ - 1 + b]);
-      }
-      if (popc_below(KMASK, b) & 1) {
+      offset_candidates<B>(W, T, c_col_hd[hi++], vn, vnE, vnO, nz2, cand);
+      if constexpr (popc_below(KMASK, B) & 1) {
 #pragma unroll
         for (int k = 0; k < KZ; ++k) acc[k] = fminf(fminf(acc[k], pend[k]), cand[k]);
       } else {
@@ -221,10 +228,39 @@ __device__ __forceinline__ void relax_column(const float (&W)[WIN], const float 
         for (int k = 0; k < KZ; ++k) pend[k] = cand[k];
       }
     }
+    relax_offsets_from<KMASK, B + 1>(W, T, hi, vn, vnE, vnO, nz2, acc, pend);
   }
-  if (popc_below(KMASK, 2 * ZHALO + 1) & 1) {
+}
+
+// The arithmetic contract, once: cand = fl(fl(hd * fl(v_n + v_m)) + tt_m); acc = min(acc, cand).
+// Node pairs (2j,2j+1) for even window shifts, (2j+1,2j+2) + two scalar ends for odd shifts, so
+// that the window operands are always naturally aligned register pairs.  Candidates of two
+// consecutive offsets are folded with one 3-input min (FMNMX3).
+template <uint32_t KMASK>
+__device__ __forceinline__ void relax_column(const float (&W)[WIN], const float (&T)[WIN], int hi,
+                                             const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                             const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
+  float pend[KZ];
+  relax_offsets_from<KMASK, 0>(W, T, hi, vn, vnE, vnO, nz2, acc, pend);
+  if constexpr (popc_below(KMASK, 2 * ZHALO + 1) & 1) {
 #pragma unroll
     for (int k = 0; k < KZ; ++k) acc[k] = fminf(acc[k], pend[k]);
+  }
+}
+
+// generic (runtime-mask) counterpart: one uniform branch per possible k offset
+template <int B>
+__device__ __forceinline__ void relax_offsets_runtime(uint32_t kmask, const float (&W)[WIN], const float (&T)[WIN],
+                                                      int& hi, const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
+                                                      const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
+  if constexpr (B <= 2 * ZHALO) {
+    if (kmask & (1u << B)) {
+      float cand[KZ];
+      offset_candidates<B>(W, T, c_col_hd[hi++], vn, vnE, vnO, nz2, cand);
+#pragma unroll
+      for (int k = 0; k < KZ; ++k) acc[k] = fminf(acc[k], cand[k]);
+    }
+    relax_offsets_runtime<B + 1>(kmask, W, T, hi, vn, vnE, vnO, nz2, acc);
   }
 }
 
@@ -298,6 +334,12 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
     float W[WIN], T[WIN];  // granules a column does not touch keep stale, never-read values
 #pragma unroll
     for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
+    u64 gE[KZ / 2], gO[KZ / 2 - 1];
+#pragma unroll
+    for (int j = 0; j < KZ / 2; ++j) gE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < KZ / 2 - 1; ++j) gO[j] = pack2(vn[2 * j + 1], vn[2 * j + 2]);
+    const u64 gnz2 = pack2(a.neg_zero, a.neg_zero);
     for (int c = 0; c < a.ncols; ++c) {
       const ColumnDev col = c_cols[c];
       const float* pv = sv + b0 + col.soff;
@@ -312,17 +354,7 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
         }
       }
       int hi = col.hd_begin;
-#pragma unroll
-      for (int b = 0; b <= 2 * ZHALO; ++b) {
-        if (col.kmask & (1u << b)) {
-          const float hd = c_col_hd[hi++];
-#pragma unroll
-          for (int k = 0; k < KZ; ++k) {
-            const float delay = __fmul_rn(hd, __fadd_rn(vn[k], W[k + b]));
-            acc[k] = fminf(acc[k], __fadd_rn(delay, T[k + b]));
-          }
-        }
-      }
+      relax_offsets_runtime<0>(col.kmask, W, T, hi, vn, gE, gO, gnz2, acc);
     }
   } else {
     u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
