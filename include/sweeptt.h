@@ -191,11 +191,19 @@ int sweeptt_solve_slabs(const float *slowness, int nx, int ny, int nz, const str
                         int starsize, struct START start, float *tt_out, const sweeptt_opts *opts,
                         sweeptt_stats *stats);
 
+/* Same, but every slab loads only its own planes (+ ghost planes) from the .vbox file with the subset
+ * reader (include/velocityboxfiler.h:741) -- what mpi/16partsmpi.c would need for models that do not
+ * fit one node's memory.  Model dimensions come from the file header. */
+int sweeptt_solve_slabs_vbox(const char *vbox_path, const struct FS *fs, int starsize, struct START start,
+                             float *tt_out, const sweeptt_opts *opts, sweeptt_stats *stats);
+
 /* ---- file formats (drop-in surface of the CLI) ---------------------------- */
 
 /* include/velocityboxfiler.h:631 vbfileloadbinary: *slowness is malloc'd (free with
  * sweeptt_free). Fails on bad magic, short file or checksum mismatch (:540-547,:727-732). */
 int sweeptt_vbox_load(const char *path, float **slowness, int origin[3], int dims[3]);
+/* include/velocityboxfiler.h:511 vbfileopenbinary: header only (dimensions of the stored box). */
+int sweeptt_vbox_dims(const char *path, int dims[3]);
 /* include/velocityboxfiler.h:310 vbfilestorebinary (byte-identical output). */
 int sweeptt_vbox_store(const char *path, const float *slowness, const int origin[3],
                        const int dims[3]);

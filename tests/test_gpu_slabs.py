@@ -47,6 +47,18 @@ def test_slabs_equal_single_device_on_a_larger_box():
     assert_bit_equal(tt, one[0])
 
 
+def test_slabs_straight_from_a_vbox_file(tmp_path):
+    """Every slab loads only its planes (+ ghosts) with the subset reader."""
+    dims = (30, 22, 19)
+    v = W.heterogeneous_field(dims, seed=8)
+    P.vbox_store(tmp_path / "m.vbox", v, origin=(1, 1, 1))
+    off, start = W.star("818"), (4, 20, 18)
+    ref, _, _ = oracle.solve(v, off, start)
+    for axis in (0, 1, 2):
+        tt, _ = P.solve_slabs_vbox(tmp_path / "m.vbox", off, start, num_slabs=3, slab_axis=axis)
+        assert_bit_equal(tt, ref, f"axis {axis}")
+
+
 def test_slab_argument_errors():
     v = W.random_field((6, 6, 6))
     with pytest.raises(P.SweepError, match="more slabs"):

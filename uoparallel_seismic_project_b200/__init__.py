@@ -19,6 +19,7 @@ from .api import (  # noqa: F401
     make_star,
     solve,
     solve_slabs,
+    solve_slabs_vbox,
     star_load,
     starts_load,
     text_load,

@@ -86,6 +86,7 @@ _EXPORTS = [
     "sweeptt_create", "sweeptt_destroy", "sweeptt_set_stream", "sweeptt_set_model", "sweeptt_set_star",
     "sweeptt_set_sources", "sweeptt_run", "sweeptt_step", "sweeptt_reset", "sweeptt_get_tt", "sweeptt_put_tt",
     "sweeptt_count_violations", "sweeptt_relaxations_per_round", "sweeptt_pool_bytes", "sweeptt_solve_slabs",
+    "sweeptt_solve_slabs_vbox", "sweeptt_vbox_dims",
     "sweeptt_vbox_load", "sweeptt_vbox_store", "sweeptt_vbox_load_subset", "sweeptt_text_load",
     "sweeptt_star_load", "sweeptt_starts_load", "sweeptt_write_output_tt", "sweeptt_free",
 ]
@@ -131,6 +132,9 @@ def load_library() -> C.CDLL:
     lib.sweeptt_pool_bytes.restype = C.c_size_t
     lib.sweeptt_solve_slabs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FS), C.c_int, START,
                                         C.c_void_p, C.POINTER(_Opts), C.POINTER(_Stats)]
+    lib.sweeptt_solve_slabs_vbox.argtypes = [C.c_char_p, C.POINTER(FS), C.c_int, START, C.c_void_p, C.POINTER(_Opts),
+                                             C.POINTER(_Stats)]
+    lib.sweeptt_vbox_dims.argtypes = [C.c_char_p, ip]
     lib.sweeptt_vbox_load.argtypes = [C.c_char_p, C.POINTER(fp), ip, ip]
     lib.sweeptt_vbox_store.argtypes = [C.c_char_p, C.c_void_p, ip, ip]
     lib.sweeptt_vbox_load_subset.argtypes = [C.c_char_p, ip, ip, C.POINTER(fp)]
@@ -245,6 +249,21 @@ def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, de
     s = _Stats()
     _check(lib.sweeptt_solve_slabs(v.ctypes.data, nx, ny, nz, fs, len(fs), st, out.ctypes.data, C.byref(o), C.byref(s)),
            "sweeptt_solve_slabs")
+    return out, SweepStats._from(s)
+
+
+def solve_slabs_vbox(path, star, start, *, num_slabs: int, slab_axis: int = 0, delta: float = 10.0):
+    """Like solve_slabs, but every slab reads only its planes from the .vbox file (subset loader)."""
+    lib = load_library()
+    d = (C.c_int * 3)()
+    _check(lib.sweeptt_vbox_dims(os.fsencode(path), d), "sweeptt_vbox_dims")
+    fs = _as_star(star, delta)
+    st = START(int(start[0]), int(start[1]), int(start[2]))
+    out = np.empty(tuple(d), np.float32)
+    o = _opts(num_devices=num_slabs, slab_axis=slab_axis)
+    s = _Stats()
+    _check(lib.sweeptt_solve_slabs_vbox(os.fsencode(path), fs, len(fs), st, out.ctypes.data, C.byref(o), C.byref(s)),
+           "sweeptt_solve_slabs_vbox")
     return out, SweepStats._from(s)
 
 

@@ -9,7 +9,8 @@
 //     dependent;
 //   * vfile may be a .vbox (serial_new) or either text dialect (cuda/, old/wavefront-openmp);
 //   * no STARTMAX / FSMAX / MODELMAX limits; start points are range-checked.
-// Optional environment: SWEEPTT_DEVICES=n (shard sources over n GPUs), SWEEPTT_TT_BIN=path
+// Optional environment: SWEEPTT_DEVICES=n (shard sources over n GPUs), SWEEPTT_SLABS=n (one grid in n
+// slabs over the GPUs, single start point files only), SWEEPTT_TT_BIN=path
 // (also dump raw float32 fields), SWEEPTT_NO_OUTPUT=1 (skip output.tt), SWEEPTT_KERNEL=simple.
 #include <cmath>
 #include <cstdio>
@@ -103,7 +104,18 @@ int main(int argc, char* argv[]) {
   sweeptt_stats st;
   std::printf("sweep 1 begin\n");
   std::fflush(stdout);
-  if (!sweeptt_solve(slow, nx, ny, nz, fs, starsize, starts, numstart, tt.data(), &opts, &st)) {
+  int ok;
+  const char* slabs = std::getenv("SWEEPTT_SLABS");
+  if (slabs && std::atoi(slabs) > 1) {
+    // one huge grid: slab decomposition, one start point at a time (mpi/16partsmpi.c scheme)
+    opts.num_devices = std::atoi(slabs);
+    if (const char* ax = std::getenv("SWEEPTT_SLAB_AXIS")) opts.slab_axis = std::atoi(ax);
+    ok = 1;
+    for (int s = 0; s < numstart && ok; ++s) ok = sweeptt_solve_slabs(slow, nx, ny, nz, fs, starsize, starts[s], tt[s], &opts, &st);
+  } else {
+    ok = sweeptt_solve(slow, nx, ny, nz, fs, starsize, starts, numstart, tt.data(), &opts, &st);
+  }
+  if (!ok) {
     std::printf("sweep failed: %s\n", sweeptt_last_error());
     return 1;
   }

@@ -131,6 +131,17 @@ extern "C" int sweeptt_vbox_load(const char* path, float** slowness, int origin[
   return 1;
 }
 
+// header only: include/velocityboxfiler.h:511-616 (vbfileopenbinary)
+extern "C" int sweeptt_vbox_dims(const char* path, int dims[3]) {
+  if (!path || !dims) return sweeptt::set_error("sweeptt_vbox_dims: null argument");
+  VboxHeader h;
+  FILE* f = open_vbox(path, &h);
+  if (!f) return 0;
+  std::fclose(f);
+  for (int a = 0; a < 3; ++a) dims[a] = h.dims[a];
+  return 1;
+}
+
 extern "C" int sweeptt_vbox_store(const char* path, const float* slowness, const int origin[3], const int dims[3]) {
   if (!path || !slowness || !dims) return sweeptt::set_error("sweeptt_vbox_store: null argument");
   FILE* f = std::fopen(path, "wb");

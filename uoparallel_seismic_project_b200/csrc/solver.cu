@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <mutex>
@@ -1209,9 +1210,11 @@ struct Slab {
 };
 }  // namespace
 
-extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz, const struct FS* fs, int starsize,
-                                   struct START start, float* tt_out, const sweeptt_opts* opts, sweeptt_stats* stats) {
-  if (!slowness || !fs || !tt_out) return fail("sweeptt_solve_slabs: null argument");
+// `fetch(origin, dims, dst)` fills dst with the caller-order sub-box of the slowness model
+static int solve_slabs_impl(const std::function<int(const int*, const int*, float*)>& fetch, int nx, int ny, int nz,
+                            const struct FS* fs, int starsize, struct START start, float* tt_out,
+                            const sweeptt_opts* opts, sweeptt_stats* stats) {
+  if (!fs || !tt_out) return fail("sweeptt_solve_slabs: null argument");
   sweeptt_opts o{};
   if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof o, opts->struct_size > 0 ? opts->struct_size : sizeof o));
   const int ndev = sweeptt_device_count();
@@ -1252,12 +1255,11 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
     int sub[3] = {nx, ny, nz};
     sub[axis] = sl.bhi - sl.blo;
     std::vector<float> box((size_t)sub[0] * sub[1] * sub[2]);
-    for (int x = 0; x < sub[0]; ++x)
-      for (int y = 0; y < sub[1]; ++y) {
-        const int gx = x + (axis == 0 ? sl.blo : 0), gy = y + (axis == 1 ? sl.blo : 0), gz = (axis == 2 ? sl.blo : 0);
-        std::memcpy(&box[((size_t)x * sub[1] + y) * sub[2]], slowness + gx * stride[0] + gy * stride[1] + gz,
-                    sizeof(float) * sub[2]);
-      }
+    {
+      int org[3] = {0, 0, 0};
+      org[axis] = sl.blo;
+      if (!fetch(org, sub, box.data())) { cleanup(); return 0; }
+    }
     START local = start;
     (axis == 0 ? local.i : axis == 1 ? local.j : local.k) -= sl.blo;
     if (!sweeptt_set_model(sl.ctx, box.data(), sub[0], sub[1], sub[2]) || !sweeptt_set_star(sl.ctx, fs, starsize) ||
@@ -1371,4 +1373,35 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
   if (stats) *stats = total;
   cleanup();
   return 1;
+}
+
+extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz, const struct FS* fs, int starsize,
+                                   struct START start, float* tt_out, const sweeptt_opts* opts, sweeptt_stats* stats) {
+  if (!slowness) return fail("sweeptt_solve_slabs: null argument");
+  auto fetch = [&](const int* org, const int* dims, float* dst) -> int {
+    for (int x = 0; x < dims[0]; ++x)
+      for (int y = 0; y < dims[1]; ++y)
+        std::memcpy(dst + ((size_t)x * dims[1] + y) * dims[2],
+                    slowness + ((size_t)(x + org[0]) * ny + (y + org[1])) * nz + org[2], sizeof(float) * dims[2]);
+    return 1;
+  };
+  return solve_slabs_impl(fetch, nx, ny, nz, fs, starsize, start, tt_out, opts, stats);
+}
+
+// Each slab reads only its own planes (+ ghost planes) straight from the .vbox file with the subset
+// loader (include/velocityboxfiler.h:741 vbfileloadbinarysubset) -- the full model never has to fit
+// in host memory at once.
+extern "C" int sweeptt_solve_slabs_vbox(const char* vbox_path, const struct FS* fs, int starsize, struct START start,
+                                        float* tt_out, const sweeptt_opts* opts, sweeptt_stats* stats) {
+  if (!vbox_path) return fail("sweeptt_solve_slabs_vbox: null argument");
+  int dims[3];
+  if (!sweeptt_vbox_dims(vbox_path, dims)) return 0;
+  auto fetch = [&](const int* org, const int* d, float* dst) -> int {
+    float* sub = nullptr;
+    if (!sweeptt_vbox_load_subset(vbox_path, org, d, &sub)) return 0;
+    std::memcpy(dst, sub, sizeof(float) * (size_t)d[0] * d[1] * d[2]);
+    sweeptt_free(sub);
+    return 1;
+  };
+  return solve_slabs_impl(fetch, dims[0], dims[1], dims[2], fs, starsize, start, tt_out, opts, stats);
 }
