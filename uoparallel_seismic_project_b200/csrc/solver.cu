@@ -298,8 +298,6 @@ extern "C" int sweeptt_set_stream(sweeptt_ctx* c, void* cuda_stream) {
   return 1;
 }
 
-static int round_up(int a, int b) { return (a + b - 1) / b * b; }
-
 static int ensure_stage(sweeptt_ctx* c, size_t floats) {
   if (c->stage_floats >= floats) return 1;
   dev_free(c, c->d_stage, c->stage_floats * 4);
