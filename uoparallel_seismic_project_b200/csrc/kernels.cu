@@ -386,6 +386,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   __shared__ int s_tile;
   __shared__ unsigned s_tmin;   // float bits of the smallest travel time this tile lowered
   __shared__ unsigned s_zmask;  // which z chunks changed
+  __shared__ unsigned s_tmax;   // float bits of the largest travel time of the tile's in-grid nodes after this visit
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wq = tid >> 5;  // wq: warp index in the CTA (0 .. 8*SPLIT-1)
@@ -415,8 +416,6 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     if (tid == 0) {
       const unsigned i = atomicAdd(&S->cursor, 1u);
       s_tile = (i < cnt) ? (int)wl[i] : -1;
-      s_tmin = 0x7f800000u;
-      s_zmask = 0u;
     }
     __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile
     const int tile = s_tile;
@@ -429,6 +428,11 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;  // logical coords of the tile interior
 
     if (tid == 0) {
+      // per-tile reduction cells: reset here, i.e. after the barrier that ends the previous tile's
+      // reads and before the mbarrier arrive that every other thread's first update is ordered behind
+      s_tmin = 0x7f800000u;
+      s_zmask = 0u;
+      s_tmax = 0u;
       // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
       mbar_expect_tx(&bar, 2u * sizeof(float) * D::BOX_FLOATS);
       tma_load_3d(sv, &tm_slow, &bar, z0 + AZ - ZHALO, y0 + AY - RXY, x0 + AX - RXY);
@@ -541,7 +545,16 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       }
       // warp-level reduction of "what changed": travel times are >= 0, so float order == uint order
       const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(tmin));
+      // largest travel time among this unit's in-grid nodes (the downwind filter below)
+      float tmx = 0.f;
+      if (gx < a.g.nx && gy < a.g.ny) {
+#pragma unroll
+        for (int k = 0; k < KZ; ++k)
+          if (gz + k < a.g.nz) tmx = fmaxf(tmx, acc[k]);
+      }
+      const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmx));
       if (lane == 0) {
+        atomicMax(&s_tmax, wmax);
         atomicAdd(&S->units_run, (unsigned long long)reps);
         if (wmin != 0x7f800000u) {
           atomicAdd(&S->units_changed, 1ull);
@@ -553,20 +566,31 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
 
     // block-wide "anything changed" (also the barrier that ends all smem reads of this tile)
     const int any = __syncthreads_or(changed);
+    const unsigned tile_tmin = s_tmin, tile_zmask = s_zmask, tile_tmax = s_tmax;
     if (any && tid < 27) {
       // a changed node reaches R <= 7 cells: every x/y neighbour tile (8 wide) is affected, the
       // z neighbours (32 long) only when the first / last z chunk changed; the tile itself only
       // needs another visit if its last in-tile pass still changed something
       const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
       const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-      const unsigned zm = s_zmask;
+      const unsigned zm = tile_zmask;
       bool reach = (dz == 0) || (dz < 0 && (zm & 1u)) || (dz > 0 && (zm & (1u << (TZ / KZ - 1))));
       if (tid == 13 && !last_pass_changed) reach = false;  // self
-      if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
-        atomicMin(&a.key[(size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz], s_tmin);
+      if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
+        const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
+        // Downwind filter: every candidate that one of our lowered nodes can offer is
+        // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
+        // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
+        // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
+        bool useful = true;
+        if (a.tmax != nullptr && tid != 13)
+          useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < a.tmax[u];
+        if (useful) atomicMin(&a.key[u], tile_tmin);
+      }
     }
     if (tid == 32) {
       const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
+      if (a.tmax != nullptr) a.tmax[(size_t)s * ntiles + tpos] = tile_tmax;
       atomicAdd(&S->tile_visits, 1ull);
       atomicAdd(&S->pulls, a.tile_pulls[tpos] * (unsigned long long)reps);
       if (any) atomicMax(&S->last_changed_round, round + 1);
@@ -753,6 +777,29 @@ __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict
         padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)];
   }
 }
+// smallest slowness of the model (bits in out[0]; out[1] != 0 when a value is negative or NaN, which
+// switches the downwind filter off): feeds RelaxArgs::dmin
+__global__ void min_slowness_kernel(const float* __restrict__ dense, long long n, unsigned* out) {
+  unsigned m = 0x7f800000u, bad = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = dense[i];
+    if (v >= 0.f) m = min(m, __float_as_uint(v)); else bad = 1u;
+  }
+  m = __reduce_min_sync(0xffffffffu, m);
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&out[0], m);
+    if (bad) atomicOr(&out[1], 1u);
+  }
+}
+cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out2, cudaStream_t stream) {
+  const unsigned init[2] = {0x7f800000u, 0u};
+  cudaError_t e = cudaMemcpyAsync(out2, init, sizeof init, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  min_slowness_kernel<<<1184, 256, 0, stream>>>(dense, n, out2);
+  return cudaGetLastError();
+}
+
 // one block per source: tt[start] = 0 and the 27 tiles around the start's tile go on list 0
 __global__ void init_sources_kernel(const RelaxArgs a) {
   const int s = blockIdx.x;
@@ -1042,6 +1089,11 @@ cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t
   init_state_kernel<<<1, 1, 0, stream>>>(st, max_rounds);
   return cudaGetLastError();
 }
+cudaError_t launch_fill_tmax(const RelaxArgs& a, cudaStream_t stream) {
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  fill_u32_kernel<<<(unsigned)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(a.tmax, (long long)total, 0x7f800000u);
+  return cudaGetLastError();
+}
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {
   init_state_kernel<<<1, 1, 0, stream>>>(a.st, max_rounds);
   cudaError_t e = launch_fill(a.tt, (long long)a.nsrc * a.g.vol, std::numeric_limits<float>::infinity(), stream);
@@ -1051,6 +1103,10 @@ cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream
   fill_u32_kernel<<<(unsigned)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(a.key, (long long)total, 0x7f800000u);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (a.tmax != nullptr) {
+    e = launch_fill_tmax(a, stream);
+    if (e != cudaSuccess) return e;
+  }
   init_sources_kernel<<<a.nsrc, 32, 0, stream>>>(a);
   return cudaGetLastError();
 }

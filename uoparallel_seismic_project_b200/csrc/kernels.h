@@ -39,6 +39,9 @@ struct RelaxArgs {
   unsigned cap;
   unsigned* key;               // nsrc * ntiles activation keys: float bits of the smallest travel time
                                // that changed next to the tile since it was last relaxed; INF = clean
+  unsigned* tmax;              // nsrc * ntiles: float bits of an upper bound of each tile's largest in-grid travel
+                               // time (INF until the tile was relaxed with every node reached); nullptr = no filter
+  float dmin;                  // lower bound (>= 0) of every edge delay fl(hd*fl(v_n+v_m)) of this model and star
   float bucket;                // only tiles with key <= (smallest key) + bucket run in a round; <0 = all
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
@@ -74,6 +77,10 @@ cudaError_t launch_pad_box(const float* dense, float* padded, BoxGeom g, cudaStr
 cudaError_t launch_unpad_box(const float* padded, float* dense, BoxGeom g, cudaStream_t stream);
 // tt := INF everywhere, 0 at each start; state, flags and the first work list reset.
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream);
+// out2[0] = float bits of the smallest slowness of the dense staged model, out2[1] != 0 if any value is negative/NaN
+cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out2, cudaStream_t stream);
+// tmax[] := INF (call whenever travel times were overwritten from outside, e.g. sweeptt_put_tt)
+cudaError_t launch_fill_tmax(const RelaxArgs& a, cudaStream_t stream);
 cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t stream);
 
 }  // namespace sweeptt

@@ -141,6 +141,8 @@ struct sweeptt_ctx {
   SolveState* h_state = nullptr;  // pinned mirror
   unsigned* d_worklist = nullptr;
   unsigned* d_key = nullptr;   // per-tile activation keys
+  unsigned* d_tmax = nullptr;  // per-tile upper bound of the largest travel time (downwind filter)
+  float min_slowness = 0.f;    // exact minimum of the model (device reduction); < 0: negative/NaN values present
   float bucket = -1.f;         // bucket width in travel-time units (<0: relax every dirty tile each round)
   double mean_slowness = 0;
   size_t tiles_cap = 0;  // nsrc*ntiles the lists/flags were sized for
@@ -276,7 +278,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
-  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
+  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -375,6 +377,17 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   CK(launch_fill(c->d_slow, g.vol, std::numeric_limits<float>::infinity(), c->stream));
   CK(cudaMemcpyAsync(c->d_stage, slowness, dense * 4, cudaMemcpyHostToDevice, c->stream));
   CK(launch_pad_box(c->d_stage, c->d_slow, g, c->stream));
+  {
+    // exact minimum of the model: lower bound of every edge delay for the downwind filter
+    unsigned r[2] = {0, 1};
+    CK(launch_min_slowness(c->d_stage, (long long)dense, reinterpret_cast<unsigned*>(c->d_viol), c->stream));
+    CK(cudaMemcpyAsync(r, c->d_viol, sizeof r, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float vmin;
+    std::memcpy(&vmin, &r[0], 4);
+    c->min_slowness = (r[1] || !std::isfinite(vmin)) ? -1.f : vmin;
+    invalidate_graph(c);
+  }
   c->have_model = true;
   if (c->have_star) {
     if (perm_changed) {  // the star tables are kept in kernel axis order
@@ -655,10 +668,12 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
   if (ntiles * numstart > c->tiles_cap) {
     dev_free(c, c->d_worklist, c->tiles_cap * 8);
     dev_free(c, c->d_key, (c->tiles_cap + 4) * 4);
-    c->d_worklist = nullptr; c->d_key = nullptr;
+    dev_free(c, c->d_tmax, (c->tiles_cap + 4) * 4);
+    c->d_worklist = nullptr; c->d_key = nullptr; c->d_tmax = nullptr;
     c->tiles_cap = ntiles * numstart;
     if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 8)) return 0;
     if (!dev_alloc(c, (void**)&c->d_key, (c->tiles_cap + 4) * 4)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_tmax, (c->tiles_cap + 4) * 4)) return 0;
     invalidate_graph(c);
   }
   if (numstart != c->nsrc) invalidate_graph(c);
@@ -684,6 +699,16 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.worklist = c->d_worklist;
   a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
   a.key = c->d_key;
+  {
+    // downwind filter (kernels.cu): needs non-negative slowness; dmin = fl(hd_min * fl(vmin + vmin)) bounds
+    // every fl(hd * fl(v_n + v_m)) from below because rounding is monotone
+    static const bool off = getenv("SWEEPTT_NO_TMAX") != nullptr;
+    a.tmax = (!off && c->min_slowness >= 0.f) ? c->d_tmax : nullptr;
+    float hdmin = std::numeric_limits<float>::infinity();
+    for (const auto& p : c->star.all) hdmin = std::min(hdmin, p.hd);
+    const float two_v = c->min_slowness + c->min_slowness;
+    a.dmin = (a.tmax && std::isfinite(hdmin) && hdmin > 0.f) ? hdmin * two_v : 0.f;
+  }
   a.bucket = c->bucket;
   a.tile_pulls = c->d_tile_pulls;
   a.ncols = (int)c->dev_columns.size();
@@ -803,6 +828,7 @@ static RelaxArgs group_args(sweeptt_ctx* c, int g) {
   a.cap = (unsigned)(ntiles * G.ns);
   a.worklist = c->d_worklist + 2 * ntiles * G.s0;  // each group owns 2*cap consecutive entries
   a.key = c->d_key + ntiles * G.s0;
+  if (a.tmax) a.tmax = c->d_tmax + ntiles * G.s0;
   return a;
 }
 
@@ -1045,6 +1071,10 @@ extern "C" int sweeptt_put_tt(sweeptt_ctx* c, int s, const float* in) {
   // (the pending work list is replaced, so mark every source's tiles, not only this one's)
   const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
   CK(cudaMemsetAsync(c->d_key, 0, ntiles * c->nsrc * 4, c->stream));  // key 0.0 = relax now
+  {
+    const RelaxArgs a = make_args(c);
+    if (a.tmax) CK(launch_fill_tmax(a, c->stream));  // the stored bounds no longer hold
+  }
   CK(launch_compact(make_args(c), 0, c->stream));  // folds the marks into the next work list
   CK(cudaStreamSynchronize(c->stream));
   return 1;
