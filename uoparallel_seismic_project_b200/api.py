@@ -77,6 +77,9 @@ class SweepStats:
 
 
 def lib_path() -> pathlib.Path:
+    import os
+    if os.environ.get("SWEEPTT_LIB"):  # developer override: an experimental build of the same ABI
+        return pathlib.Path(os.environ["SWEEPTT_LIB"])
     return _PKG / "lib" / "libsweeptt.so"
 
 

@@ -5,18 +5,25 @@
 namespace sweeptt {
 
 // ---- tile shape of the tiled kernel -------------------------------------------------
-// Interior tile TX x TY x TZ nodes; each thread owns KZ consecutive z nodes of one (x,y)
-// column (register window along the fastest axis).  256 threads per CTA.
-#ifndef SWEEPTT_KZ
-#define SWEEPTT_KZ 8
+// Interior tile TX x TY x TZ nodes.  The work unit of a warp is a 4 x 8 x 8 block: lane ->
+// (x within the 4-wide unit, y), each thread owns the KZ = 8 consecutive z nodes of its (x,y)
+// column (register window along the fastest axis).  A tile holds UNITS = TX/4 units; the star's
+// columns of every unit are shared out between the CTA's compute warps.  Small tiles keep the
+// activation granularity (one key per tile) close to the star radius, which is what bounds the
+// number of times a node is re-relaxed while the front crosses it.
+#ifndef SWEEPTT_TX
+#define SWEEPTT_TX 8
 #endif
-constexpr int TX = 8, TY = 8, TZ = 32, KZ = SWEEPTT_KZ;
-constexpr int ZCHUNKS = TZ / KZ;
+constexpr int TX = SWEEPTT_TX, TY = 8, TZ = 8, KZ = 8;
+static_assert(TX == 4 || TX == 8, "a tile is one or two 4x8x8 units");
+constexpr int UNITS = TX / 4;
 constexpr int ZHALO = 8;                 // z halo staged on both sides (16-byte aligned)
-constexpr int SZD = TZ + 2 * ZHALO + 4;  // smem/TMA row length: 52 floats; 52/4 = 13 is odd,
+constexpr int SZD = TZ + 2 * ZHALO + 4;  // smem/TMA row length: 28 floats; 28/4 = 7 is odd,
                                          // which makes the quarter-warp LDS.128 conflict-free
 constexpr int WIN = KZ + 2 * ZHALO;      // 24-float register window per (i,j) column
-constexpr int TILE_THREADS = TX * TY * (TZ / KZ);
+constexpr int MAX_WARPS = 16;            // compute warps per CTA (one more warp feeds the TMA pipeline)
+constexpr int XREACH = (7 + TX - 1) / TX;  // tiles that a changed node (reach <= 7 nodes) can affect along x
+constexpr int NMARK = (2 * XREACH + 1) * 9;
 
 // ---- padded device float box ----------------------------------------------------------
 // Logical node (x,y,z) lives at padded index ((x+AX)*py + (y+AY))*pz + (z+AZ).

@@ -43,10 +43,19 @@ namespace sweeptt {
 __constant__ ColumnDev c_cols[MAX_COLUMNS];
 __constant__ float c_col_hd[MAX_COL_HD];
 __constant__ ExtraDev c_extra[MAX_EXTRA];
+// c_psplit[g * (MAX_WARPS + 1) + f]: first column of fine part f (of nw) within pattern group g; part p of
+// P = nw / nlive parts runs the columns [c_psplit[g][p * nlive], c_psplit[g][(p + 1) * nlive]) of EVERY group,
+// so all warps walk the pattern code blocks in the same order (instruction-cache locality) and the host
+// can balance the parts' total cost
+__constant__ unsigned short c_psplit[MAX_PATTERNS * (MAX_WARPS + 1)];
 
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, cudaStream_t stream) {
+                                  const ExtraDev* extra, int nextra, const unsigned short* psplit, int npsplit,
+                                  cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
+  if (npsplit > 0)
+    e = cudaMemcpyToSymbolAsync(c_psplit, psplit, sizeof(unsigned short) * npsplit, 0, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
   if (ncols > 0)
     e = cudaMemcpyToSymbolAsync(c_cols, cols, sizeof(ColumnDev) * ncols, 0, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess && nhd > 0)
@@ -113,11 +122,34 @@ struct TileDims {
   static constexpr int SXD = TX + 2 * RXY;
   static constexpr int SYD = TY + 2 * RXY;
   static constexpr int BOX_FLOATS = SXD * SYD * SZD;
-  // second box starts on a 1024-byte boundary (TMA destinations must be 128-byte aligned)
-  static constexpr int BOX_STRIDE = (BOX_FLOATS * 4 + 1023) / 1024 * 1024 / 4;
-  static constexpr size_t SMEM = sizeof(float) * (BOX_STRIDE + BOX_FLOATS) + 1024;  // + alignment slack
-  static constexpr size_t SMEM_SPLIT = sizeof(float) * (2 * BOX_STRIDE + TILE_THREADS * KZ) + 1024;
+  // every staged box starts on a 128-byte boundary (TMA destination alignment)
+  static constexpr int BOX_STRIDE = (BOX_FLOATS * 4 + 127) / 128 * 128 / 4;
+  static constexpr int ACC_WORDS = UNITS * KZ * 32;  // per-node min cells the star's parts are combined through
+  // 2 pipeline stages x (slowness box + travel-time box) + combine cells + alignment slack
+  static constexpr size_t SMEM = sizeof(float) * (4 * BOX_STRIDE + ACC_WORDS) + 128;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barriers over the compute warps only (the TMA producer warp never joins them)
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ int named_sync_or(int id, int nthreads, int pred) {
+  int r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.s32 q, %3, 0;\n\t"
+      "bar.red.or.pred p, %1, %2, q;\n\t"
+      "selp.s32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"(pred)
+      : "memory");
+  return r;
+}
 
 // ---- column phase -------------------------------------------------------------------------
 // One (i,j) column of the star = one 24-float register window of slowness and of travel time
@@ -156,6 +188,18 @@ __device__ __forceinline__ void load_window(const float* __restrict__ pv, const 
 // the following add.  tests/test_sass.py greps the SASS.
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+// A pair of consecutive floats read from shared memory at a 4-byte (not 8-byte) aligned address with
+// VOLATILE loads: ptxas cannot re-materialise a volatile load, so the pair stays in registers.  Used for
+// the odd-aligned slowness pairs (vn[1],vn[2]), ...: built with plain moves, ptxas rebuilds them with two
+// MOVs in front of every pattern block's uses (measured: 11 % of all executed instructions).
+__device__ __forceinline__ u64 lds_pair_keep(const float* p) {
+  float lo, hi;
+  const uint32_t addr = smem_u32(p);
+  asm volatile("ld.volatile.shared.f32 %0, [%2];\n\tld.volatile.shared.f32 %1, [%2+4];" : "=f"(lo), "=f"(hi) : "r"(addr));
   u64 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
@@ -200,7 +244,6 @@ __device__ __forceinline__ void offset_candidates(const float (&W)[WIN], const f
   } else {
 #pragma unroll
     for (int j = 0; j < KZ / 2 - 1; ++j) {
-      constexpr int dummy = 0; (void)dummy;
       const int k = 2 * j + 1;
       const u64 sum = add2(vnO[j], pack2(W[k + B], W[k + B + 1]));
       const u64 c2 = add2(mul2_exact(hd2, sum, nz2), pack2(T[k + B], T[k + B + 1]));
@@ -232,10 +275,6 @@ __device__ __forceinline__ void relax_offsets_from(const float (&W)[WIN], const 
   }
 }
 
-// The arithmetic contract, once: cand = fl(fl(hd * fl(v_n + v_m)) + tt_m); acc = min(acc, cand).
-// Node pairs (2j,2j+1) for even window shifts, (2j+1,2j+2) + two scalar ends for odd shifts, so
-// that the window operands are always naturally aligned register pairs.  Candidates of two
-// consecutive offsets are folded with one 3-input min (FMNMX3).
 template <uint32_t KMASK>
 __device__ __forceinline__ void relax_column(const float (&W)[WIN], const float (&T)[WIN], int hi,
                                              const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
@@ -264,145 +303,107 @@ __device__ __forceinline__ void relax_offsets_runtime(uint32_t kmask, const floa
   }
 }
 
-#ifndef SWEEPTT_SCHED_FENCE
-#define SWEEPTT_SCHED_FENCE() ((void)0)  // measured: forcing the window loads above the FP block with __syncwarp() is SLOWER (21.7 vs 20.0 ms)
-#endif
-
-// all columns [cbeg,cend) share the compile-time pattern KMASK: branch-free unrolled blocks,
-// the next column's window is fetched (ping-pong registers) while the current one computes
+// The columns of pattern group G share the compile-time k-pattern KMASK (branch-free unrolled block);
+// this warp runs ITS sub-range [lo,hi) of them (c_psplit).  A group's half-distances are contiguous in
+// column order, so their addresses are pure arithmetic.  Window loads are single-buffered: with 16
+// warps per SM the other warps hide the shared-memory latency.
 template <uint32_t KMASK>
-__device__ __forceinline__ void run_pattern(const float* __restrict__ sv, const float* __restrict__ st, int b0,
-                                            int cbeg, int cend, const float (&vn)[KZ], const u64 (&vnE)[KZ / 2],
-                                            const u64 (&vnO)[KZ / 2 - 1], u64 nz2, float (&acc)[KZ]) {
+__device__ __forceinline__ void run_pattern_range(const float* __restrict__ sv, const float* __restrict__ st, int b0,
+                                                  int pb, int lo, int hi_, const float (&vn)[KZ],
+                                                  const u64 (&vnE)[KZ / 2], const u64 (&vnO)[KZ / 2 - 1], u64 nz2,
+                                                  float (&acc)[KZ]) {
   constexpr uint32_t GM = granules_of(KMASK);
   constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
-  // Host-side guarantees (solver.cu, upload_constants): every pattern group has an EVEN number of
-  // columns (a duplicated column is harmless: min is idempotent), the half-distances of a group
-  // are contiguous in column order, and the table has two valid spare entries at its end -- so
-  // the loop needs no tail code, hd addresses are pure arithmetic, and the column descriptors
-  // can be fetched two columns ahead of the window loads that need them (software pipeline:
-  // LDC descriptor -> LDS windows -> packed FP, each stage one column apart).
-  if (cbeg >= cend) return;
-  float Wa[WIN], Ta[WIN], Wb[WIN], Tb[WIN];
-  int hi = c_cols[cbeg].hd_begin;
-  int soffA = c_cols[cbeg].soff;
-  int soffB = c_cols[cbeg + 1].soff;
-  load_window<GM>(sv + b0 + soffA, st + b0 + soffA, Wa, Ta);
-  for (int c = cbeg; c < cend; c += 2) {
-    load_window<GM>(sv + b0 + soffB, st + b0 + soffB, Wb, Tb);
-    soffA = c_cols[c + 2].soff;
-    soffB = c_cols[c + 3].soff;
-    SWEEPTT_SCHED_FENCE();  // keeps the window loads ABOVE the FP block they overlap with (ptxas otherwise
-                            // sinks each LDS next to its first use, which exposes the smem latency)
-    relax_column<KMASK>(Wa, Ta, hi, vn, vnE, vnO, nz2, acc);
-    load_window<GM>(sv + b0 + soffA, st + b0 + soffA, Wa, Ta);
-    SWEEPTT_SCHED_FENCE();
-    relax_column<KMASK>(Wb, Tb, hi + NK, vn, vnE, vnO, nz2, acc);
-    hi += 2 * NK;
-  }
-}
-
-// SPLIT = 2: two thread groups own the same nodes and each runs HALF of every pattern's columns
-// (16 warps per SM at the same shared-memory footprint; results min-combined through smem).
-// Register budget is 128 per thread there, so the windows are single-buffered and latency is
-// hidden by the extra warps instead of the ping-pong.
-template <uint32_t KMASK>
-__device__ __forceinline__ void run_pattern_half(const float* __restrict__ sv, const float* __restrict__ st, int b0,
-                                                 int pb, int pe, int half, const float (&vn)[KZ],
-                                                 const u64 (&vnE)[KZ / 2], const u64 (&vnO)[KZ / 2 - 1], u64 nz2,
-                                                 float (&acc)[KZ]) {
-  constexpr uint32_t GM = granules_of(KMASK);
-  constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
-  if (pb >= pe) return;
-  const int mid = pb + (pe - pb) / 2;
-  const int cb = half ? mid : pb, ce = half ? pe : mid;
+  if (lo >= hi_) return;
   const int hi0 = c_cols[pb].hd_begin;
   float W[WIN], T[WIN];
-  for (int c = cb; c < ce; ++c) {
+  for (int c = lo; c < hi_; ++c) {
     const int soff = c_cols[c].soff;
     load_window<GM>(sv + b0 + soff, st + b0 + soff, W, T);
     relax_column<KMASK>(W, T, hi0 + (c - pb) * NK, vn, vnE, vnO, nz2, acc);
   }
 }
 
-template <int SPLIT, uint32_t... M>
+// `f0`,`f1`: this warp's fine-part range; `after(g)` runs after pattern group g-1 (the ring feeder's hooks)
+template <typename HOOK, uint32_t... M>
 __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
-                                              const float* __restrict__ st, int b0, const RelaxArgs& a, int half,
-                                              const float (&vn)[KZ], float (&acc)[KZ]) {
+                                              const float* __restrict__ st, int b0, const RelaxArgs& a, int f0, int f1,
+                                              const float (&vn)[KZ], float (&acc)[KZ], HOOK&& after) {
+  u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
+#pragma unroll
+  for (int j = 0; j < KZ / 2; ++j) vnE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < KZ / 2 - 1; ++j) vnO[j] = lds_pair_keep(sv + b0 + ZHALO + 2 * j + 1);  // = (vn[2j+1], vn[2j+2])
+  const u64 nz2 = pack2(a.neg_zero, a.neg_zero);
   if constexpr (sizeof...(M) == 0) {
     // generic: runtime masks (any star that fits the halo)
     float W[WIN], T[WIN];  // granules a column does not touch keep stale, never-read values
 #pragma unroll
     for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
-    u64 gE[KZ / 2], gO[KZ / 2 - 1];
+    for (int g = 0; g < a.npat; ++g) {
+      const int lo = c_psplit[g * (MAX_WARPS + 1) + f0], hi_ = c_psplit[g * (MAX_WARPS + 1) + f1];
+      for (int c = lo; c < hi_; ++c) {
+        const ColumnDev col = c_cols[c];
+        const float* pv = sv + b0 + col.soff;
+        const float* pt = st + b0 + col.soff;
 #pragma unroll
-    for (int j = 0; j < KZ / 2; ++j) gE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
-#pragma unroll
-    for (int j = 0; j < KZ / 2 - 1; ++j) gO[j] = pack2(vn[2 * j + 1], vn[2 * j + 2]);
-    const u64 gnz2 = pack2(a.neg_zero, a.neg_zero);
-    for (int c = 0; c < a.ncols; ++c) {
-      const ColumnDev col = c_cols[c];
-      const float* pv = sv + b0 + col.soff;
-      const float* pt = st + b0 + col.soff;
-#pragma unroll
-      for (int g = 0; g < WIN / 4; ++g) {
-        if (col.gmask & (1u << g)) {
-          const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * g);
-          const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * g);
-          W[4 * g] = wv.x; W[4 * g + 1] = wv.y; W[4 * g + 2] = wv.z; W[4 * g + 3] = wv.w;
-          T[4 * g] = wt.x; T[4 * g + 1] = wt.y; T[4 * g + 2] = wt.z; T[4 * g + 3] = wt.w;
+        for (int q = 0; q < WIN / 4; ++q) {
+          if (col.gmask & (1u << q)) {
+            const float4 wv = *reinterpret_cast<const float4*>(pv + 4 * q);
+            const float4 wt = *reinterpret_cast<const float4*>(pt + 4 * q);
+            W[4 * q] = wv.x; W[4 * q + 1] = wv.y; W[4 * q + 2] = wv.z; W[4 * q + 3] = wv.w;
+            T[4 * q] = wt.x; T[4 * q + 1] = wt.y; T[4 * q + 2] = wt.z; T[4 * q + 3] = wt.w;
+          }
         }
+        int hi = col.hd_begin;
+        relax_offsets_runtime<0>(col.kmask, W, T, hi, vn, vnE, vnO, nz2, acc);
       }
-      int hi = col.hd_begin;
-      relax_offsets_runtime<0>(col.kmask, W, T, hi, vn, gE, gO, gnz2, acc);
+      after(g + 1, a.npat);
     }
   } else {
-    u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
-#pragma unroll
-    for (int j = 0; j < KZ / 2; ++j) vnE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
-#pragma unroll
-    for (int j = 0; j < KZ / 2 - 1; ++j) vnO[j] = pack2(vn[2 * j + 1], vn[2 * j + 2]);
-    const u64 nz2 = pack2(a.neg_zero, a.neg_zero);
-    int p = 0;
-    if constexpr (SPLIT == 1) {
-      ((run_pattern<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], vn, vnE, vnO, nz2, acc), ++p), ...);
-    } else {
-      ((run_pattern_half<M>(sv, st, b0, a.pat_begin[p], a.pat_begin[p + 1], half, vn, vnE, vnO, nz2, acc), ++p), ...);
-    }
+    int g = 0;
+    ((run_pattern_range<M>(sv, st, b0, a.pat_begin[g], c_psplit[g * (MAX_WARPS + 1) + f0],
+                           c_psplit[g * (MAX_WARPS + 1) + f1], vn, vnE, vnO, nz2, acc),
+      ++g, after(g, (int)sizeof...(M))),
+     ...);
   }
 }
 
-template <int RXY, typename STAR, int SPLIT = 1>
-__global__ void __launch_bounds__(TILE_THREADS * SPLIT, (RXY == 7) ? 1 : 2)
+// Persistent CTA of NW warps.
+//   staging   tile ids are popped from the round's work list (one atomicAdd each) and the tile's slowness
+//             and travel-time boxes (interior + star-radius halo) are streamed into a 2-stage shared-memory
+//             ring with TMA (cp.async.bulk.tensor): tile i+1 lands while tile i is being relaxed.  Thread 0
+//             drives the ring from three points of its own column phase, so that neither the atomic nor
+//             the work-list load nor the copy is ever waited for.
+//   relaxing  a tile is UNITS 4x8x8 units; the star's columns of every live unit are shared out between
+//             NW / nlive warps ("parts", cost-balanced cut points from the host), each part keeps its
+//             KZ accumulators in registers, lowers the unit's per-node min cells in shared memory
+//             (atomicMin on the float bits: travel times are >= 0) and part 0 of the unit (the owner)
+//             finishes: start-point pin, changed test, 128-bit stores, activation of the neighbours.
+template <int RXY, typename STAR, int NW>
+__global__ void __launch_bounds__(32 * NW, (RXY == 2) ? 3 : 1)
 relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
             const __grid_constant__ RelaxArgs a) {
   using D = TileDims<RXY>;
+  constexpr int NCT = 32 * NW;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // 1024-byte aligned carve-up: [slowness box][travel-time box]
-  float* sv = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  float* st = sv + D::BOX_STRIDE;
-  float* s_comb = st + D::BOX_STRIDE;  // SPLIT == 2: [k][thread] accumulators of the second thread group
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ int s_tile;
-  __shared__ unsigned s_tmin;   // float bits of the smallest travel time this tile lowered
-  __shared__ unsigned s_zmask;  // which z chunks changed
-  __shared__ unsigned s_tmax;   // float bits of the largest travel time of the tile's in-grid nodes after this visit
+  float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  unsigned* s_acc = reinterpret_cast<unsigned*>(ring + 4 * D::BOX_STRIDE);
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ int s_tile[2];
+  __shared__ unsigned s_tmin[2];  // float bits of the smallest travel time the tile lowered
+  __shared__ unsigned s_tmax[2];  // float bits of the largest travel time of the tile's in-grid nodes
 
   const int tid = threadIdx.x;
-  const int lane = tid & 31, wq = tid >> 5;  // wq: warp index in the CTA (0 .. 8*SPLIT-1)
-  // lane -> (x within a 4-wide x half, y): a quarter-warp shares x and z chunk and spans 8
-  // consecutive y, whose rows are SZD=52 floats apart -> conflict-free LDS.128.
-  // Which (x half, z chunk) unit -- and, with SPLIT, which half of the star -- a warp works on is
-  // decided per tile from the tile's LIVE units (those with nodes inside the grid): the busy warps
-  // are always warps 0..SPLIT*nlive-1, so the four schedulers stay evenly loaded when part of a
-  // tile hangs outside the grid (e.g. nz = 51: the upper z tile has 6 live units -> 12 of 16 warps,
-  // 3 per scheduler, instead of two schedulers idling behind two full ones).
-  const int y = lane & 7;
-
+  const int lane = tid & 31;
+  const int wq = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp index, provably warp-uniform
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
     fence_mbar_init();
+    s_tmin[0] = s_tmin[1] = 0x7f800000u;
+    s_tmax[0] = s_tmax[1] = 0u;
   }
+  for (int i = tid; i < D::ACC_WORDS; i += NCT) s_acc[i] = 0x7f800000u;
   __syncthreads();
 
   SolveState* S = a.st;
@@ -412,78 +413,103 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   const int round = S->round;
   const int ntiles = a.g.ntx * a.g.nty * a.g.ntz;
 
-  for (uint32_t it = 0;; ++it) {
-    if (tid == 0) {
-      const unsigned i = atomicAdd(&S->cursor, 1u);
-      s_tile = (i < cnt) ? (int)wl[i] : -1;
+  // stage `q` of the ring <- the boxes of `tile` (or the end marker); thread 0 only
+  auto stage_tile = [&](int q, int tile) {
+    s_tile[q] = tile;
+    if (tile < 0) {
+      mbar_arrive(&full[q]);
+      return;
     }
-    __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile
-    const int tile = s_tile;
+    const int s = tile / ntiles;
+    int tp = tile - s * ntiles;
+    const int tz = tp % a.g.ntz; tp /= a.g.ntz;
+    const int ty = tp % a.g.nty;
+    const int tx = tp / a.g.nty;
+    float* sv = ring + q * 2 * D::BOX_STRIDE;
+    // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
+    mbar_expect_tx(&full[q], 2u * sizeof(float) * D::BOX_FLOATS);
+    tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY);
+    tma_load_4d(sv + D::BOX_STRIDE, &tm_tt, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY, s);
+  };
+  if (tid == 0) {
+    const unsigned i = atomicAdd(&S->cursor, 1u);
+    stage_tile(0, (i < cnt) ? (int)wl[i] : -1);
+  }
+
+  // lane -> (x within the 4-wide unit, y): a quarter-warp shares x and spans 8 consecutive y, whose
+  // rows are SZD = 28 floats apart -> conflict-free LDS.128.
+  const int y = lane & 7;
+  for (uint32_t it = 0;; ++it) {
+    const int q = it & 1;
+    mbar_wait(&full[q], (it >> 1) & 1);
+    const int tile = s_tile[q];
     if (tile < 0) break;
+    // stage q^1 is free (every warp is past the last barrier of the previous tile): claim the next tile
+    unsigned pop_i = 0;
+    int next_tile = -1;
+    if (tid == 0) pop_i = atomicAdd(&S->cursor, 1u);
     const int s = tile / ntiles;
     int tp = tile - s * ntiles;
     const int tz = tp % a.g.ntz; tp /= a.g.ntz;
     const int ty = tp % a.g.nty;
     const int tx = tp / a.g.nty;
     const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;  // logical coords of the tile interior
+    const float* sv = ring + q * 2 * D::BOX_STRIDE;
+    float* st = ring + q * 2 * D::BOX_STRIDE + D::BOX_STRIDE;
 
-    if (tid == 0) {
-      // per-tile reduction cells: reset here, i.e. after the barrier that ends the previous tile's
-      // reads and before the mbarrier arrive that every other thread's first update is ordered behind
-      s_tmin = 0x7f800000u;
-      s_zmask = 0u;
-      s_tmax = 0u;
-      // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
-      mbar_expect_tx(&bar, 2u * sizeof(float) * D::BOX_FLOATS);
-      tma_load_3d(sv, &tm_slow, &bar, z0 + AZ - ZHALO, y0 + AY - RXY, x0 + AX - RXY);
-      tma_load_4d(st, &tm_tt, &bar, z0 + AZ - ZHALO, y0 + AY - RXY, x0 + AX - RXY, s);
-    }
-    mbar_wait(&bar, it & 1);
-
-    // live units of this tile and this warp's assignment
-    const int nxh = (x0 + 4 < a.g.nx) ? 2 : 1;
-    const int nzc = min(ZCHUNKS, (a.g.nz - z0 + KZ - 1) / KZ);
-    const int nlive = nxh * nzc;
-    const bool warp_live = wq < SPLIT * nlive;
-    const int half = (SPLIT == 1) ? 0 : wq / nlive;  // which half of the star's columns
-    const int li = wq - half * nlive;                // live unit index
-    const int xh = li / nzc, zc = li - xh * nzc;
-    const int t = li * 32 + lane;                    // thread index within the thread group
-    const int x = (xh << 2) | (lane >> 3);
+    // live units (those with nodes inside the grid) and this warp's share of the star
+    const int nlive = (UNITS == 2 && x0 + 4 < a.g.nx) ? 2 : 1;
+    const int P = NW / nlive;
+    const int unit = wq / P, part = wq - unit * P;
+    const int f0 = part * nlive, f1 = f0 + nlive;  // fine-part range in c_psplit
+    const bool owner = part == 0;
+    const int x = (unit << 2) | (lane >> 3);
     // smem float index of this thread's window start for the (0,0) column
-    const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD + zc * KZ;
-    const int gx = x0 + x, gy = y0 + y, gz = z0 + zc * KZ;
+    const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD;
+    const int gx = x0 + x, gy = y0 + y, gz = z0;
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
-    float vn[KZ], told[KZ], acc[KZ];
-    if (warp_live) {
+    unsigned* cell = s_acc + (unit * KZ) * 32 + lane;  // cell[k * 32]
+    float vn[KZ], acc[KZ];
 #pragma unroll
-      for (int q = 0; q < KZ / 4; ++q) {
-        const float4 vv = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4 * q);
-        const float4 tv = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4 * q);
-        vn[4 * q] = vv.x; vn[4 * q + 1] = vv.y; vn[4 * q + 2] = vv.z; vn[4 * q + 3] = vv.w;
-        told[4 * q] = tv.x; told[4 * q + 1] = tv.y; told[4 * q + 2] = tv.z; told[4 * q + 3] = tv.w;
-      }
-#pragma unroll
-      for (int k = 0; k < KZ; ++k) acc[k] = half ? CUDART_INF_F : told[k];
+    for (int j = 0; j < KZ / 4; ++j) {
+      const float4 vv = *reinterpret_cast<const float4*>(sv + b0 + ZHALO + 4 * j);
+      const float4 tv = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4 * j);
+      vn[4 * j] = vv.x; vn[4 * j + 1] = vv.y; vn[4 * j + 2] = vv.z; vn[4 * j + 3] = vv.w;
+      acc[4 * j] = tv.x; acc[4 * j + 1] = tv.y; acc[4 * j + 2] = tv.z; acc[4 * j + 3] = tv.w;
     }
 
     // In-tile iterations (block Gauss-Seidel): while the tile's own nodes keep changing, publish the
-    // new values to the staged box and relax again against the same halo -- information then
-    // crosses the tile in one visit instead of one hop per round.  Every pass is a set of valid
-    // relaxations, so the fixed point is unchanged.
+    // new values to the staged box and relax again against the same halo.  Every pass is a set of
+    // valid relaxations, so the fixed point is unchanged.
+    // The values a pass started from are NOT kept in registers during the column phase: they are still
+    // in the staged box (nobody writes it meanwhile) and are read back for the comparisons.
     int reps = 0;
     int last_pass_changed = 0;
+    bool published = false;
+    unsigned lowered = 0;  // owner: bit k = node k was lowered by this visit
     for (;;) {
       int pass_changed = 0;
-      float beforeq[KZ];
-      if (warp_live) {
+      // Thread 0 feeds the ring from two points of its first pass: the work-list entry is read a few
+      // pattern groups after the atomic was issued, the copy starts a few groups later -- neither the
+      // atomic nor the load nor the copy is ever waited for.
+      const bool feeds = (tid == 0 && reps == 0);
+      columns_phase(STAR{}, sv, st, b0, a, f0, f1, vn, acc, [&](int g, int npat) {
+        const int h0 = (npat + 5) / 6, h1 = (npat + 2) / 3;
+        if (feeds) {
+          if (g == h0) next_tile = (pop_i < cnt) ? (int)wl[pop_i] : -1;
+          if (g == h1) stage_tile(q ^ 1, next_tile);
+        }
+      });
+      float bq[KZ];
 #pragma unroll
-        for (int k = 0; k < KZ; ++k) beforeq[k] = acc[k];
-        columns_phase<SPLIT>(STAR{}, sv, st, b0, a, half, vn, acc);
-
+      for (int j = 0; j < KZ / 4; ++j) {
+        const float4 tv = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4 * j);
+        bq[4 * j] = tv.x; bq[4 * j + 1] = tv.y; bq[4 * j + 2] = tv.z; bq[4 * j + 3] = tv.w;
+      }
+      if (owner) {
         // ---- pulls handled one at a time: guarded (invalid when the neighbour is the start,
         //      serial_new/...c:219-221 with :160) and duplicates ----
-        for (int e = 0; e < (half ? 0 : a.nextra); ++e) {
+        for (int e = 0; e < a.nextra; ++e) {
           const ExtraDev ex = c_extra[e];
           const float* pv = sv + b0 + ZHALO + ex.soff;
           const float* pt = st + b0 + ZHALO + ex.soff;
@@ -495,53 +521,61 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (!bad) acc[k] = fminf(acc[k], cand);
           }
         }
-        if constexpr (SPLIT == 2) {
-          if (half) {
+      } else {
+        // a part that found something lower hands it to the owner through the unit's min cells
 #pragma unroll
-            for (int k = 0; k < KZ; ++k) s_comb[k * TILE_THREADS + t] = acc[k];
-          }
-        }
+        for (int k = 0; k < KZ; ++k)
+          if (acc[k] < bq[k]) atomicMin(cell + k * 32, __float_as_uint(acc[k]));
       }
-      if constexpr (SPLIT == 2) __syncthreads();
-      if (warp_live && half == 0) {
-        if constexpr (SPLIT == 2) {
+      named_sync(1, NCT);
+      if (owner) {
 #pragma unroll
-          for (int k = 0; k < KZ; ++k) acc[k] = fminf(acc[k], s_comb[k * TILE_THREADS + t]);
+        for (int k = 0; k < KZ; ++k) {
+          const unsigned u = cell[k * 32];
+          acc[k] = fminf(acc[k], __uint_as_float(u));
+          if (u != 0x7f800000u) cell[k * 32] = 0x7f800000u;
         }
         // the start point itself is never relaxed (serial_new/...c:219-221)
         if (gx == px && gy == py) {
 #pragma unroll
           for (int k = 0; k < KZ; ++k)
-            if (gz + k == pz) acc[k] = told[k];
+            if (gz + k == pz) acc[k] = bq[k];
         }
 #pragma unroll
-        for (int k = 0; k < KZ; ++k) pass_changed |= (acc[k] < beforeq[k]);
+        for (int k = 0; k < KZ; ++k)
+          if (acc[k] < bq[k]) { pass_changed = 1; lowered |= 1u << k; }
       }
       ++reps;
-      last_pass_changed = __syncthreads_or(pass_changed);  // also: every thread is done reading the staged box
+      if (a.max_inner <= 1) break;  // one pass per visit
+      last_pass_changed = named_sync_or(2, NCT, pass_changed);  // also: every warp is done reading the staged box
       if (!last_pass_changed || reps >= a.max_inner) break;
-      if (pass_changed && half == 0) {
+      if (owner && pass_changed) {
 #pragma unroll
-        for (int q = 0; q < KZ / 4; ++q)
-          *reinterpret_cast<float4*>(st + b0 + ZHALO + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        for (int j = 0; j < KZ / 4; ++j)
+          *reinterpret_cast<float4*>(st + b0 + ZHALO + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
-      __syncthreads();
+      published = true;
+      named_sync(3, NCT);
+      if (!owner) {  // the other parts restart from the published values
+#pragma unroll
+        for (int j = 0; j < KZ / 4; ++j) {
+          const float4 tv = *reinterpret_cast<const float4*>(st + b0 + ZHALO + 4 * j);
+          acc[4 * j] = tv.x; acc[4 * j + 1] = tv.y; acc[4 * j + 2] = tv.z; acc[4 * j + 3] = tv.w;
+        }
+      }
     }
 
-    int changed = 0;
-    if (warp_live && half == 0) {
+    const int changed = owner && lowered != 0;
+    if (owner) {
       float tmin = CUDART_INF_F;
 #pragma unroll
-      for (int k = 0; k < KZ; ++k) {
-        const bool lower = acc[k] < told[k];
-        changed |= lower;
-        tmin = lower ? fminf(tmin, acc[k]) : tmin;
-      }
+      for (int k = 0; k < KZ; ++k)
+        if (lowered & (1u << k)) tmin = fminf(tmin, acc[k]);
       if (changed) {
         float* out = a.tt + (size_t)s * a.g.vol + ((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ);
 #pragma unroll
-        for (int q = 0; q < KZ / 4; ++q)
-          *reinterpret_cast<float4*>(out + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        for (int j = 0; j < KZ / 4; ++j)
+          *reinterpret_cast<float4*>(out + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
       // warp-level reduction of "what changed": travel times are >= 0, so float order == uint order
       const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(tmin));
@@ -554,28 +588,31 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       }
       const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmx));
       if (lane == 0) {
-        atomicMax(&s_tmax, wmax);
-        atomicAdd(&S->units_run, (unsigned long long)reps);
+        atomicMax(&s_tmax[q], wmax);
         if (wmin != 0x7f800000u) {
           atomicAdd(&S->units_changed, 1ull);
-          atomicMin(&s_tmin, wmin);
-          atomicOr(&s_zmask, 1u << zc);
+          atomicMin(&s_tmin[q], wmin);
         }
       }
     }
+    if (tid == 0) {  // the other stage's cells: read by everyone before this tile's first barrier, used again after the next one
+      s_tmin[q ^ 1] = 0x7f800000u;
+      s_tmax[q ^ 1] = 0u;
+    }
+    if (published) fence_proxy_async();  // generic-proxy writes to the stage precede the next TMA fill
 
     // block-wide "anything changed" (also the barrier that ends all smem reads of this tile)
-    const int any = __syncthreads_or(changed);
-    const unsigned tile_tmin = s_tmin, tile_zmask = s_zmask, tile_tmax = s_tmax;
-    if (any && tid < 27) {
-      // a changed node reaches R <= 7 cells: every x/y neighbour tile (8 wide) is affected, the
-      // z neighbours (32 long) only when the first / last z chunk changed; the tile itself only
-      // needs another visit if its last in-tile pass still changed something
-      const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
+    const int any = named_sync_or(2, NCT, changed);
+    if (a.max_inner <= 1) last_pass_changed = any;
+    const unsigned tile_tmin = s_tmin[q], tile_tmax = s_tmax[q];
+    if (any && tid < NMARK) {
+      // a changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected;
+      // the tile itself only needs another visit if its last in-tile pass still changed something
+      const int dx = tid / 9 - XREACH, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
       const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-      const unsigned zm = tile_zmask;
-      bool reach = (dz == 0) || (dz < 0 && (zm & 1u)) || (dz > 0 && (zm & (1u << (TZ / KZ - 1))));
-      if (tid == 13 && !last_pass_changed) reach = false;  // self
+      const bool self = (dx == 0 && dy == 0 && dz == 0);
+      bool reach = (abs(dx) - 1) * TX < RXY;  // x distance between the closest nodes of the two tiles
+      if (self && !last_pass_changed) reach = false;
       if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
         const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
         // Downwind filter: every candidate that one of our lowered nodes can offer is
@@ -583,15 +620,16 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
         // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
         bool useful = true;
-        if (a.tmax != nullptr && tid != 13)
+        if (a.tmax != nullptr && !self)
           useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < a.tmax[u];
         if (useful) atomicMin(&a.key[u], tile_tmin);
       }
     }
-    if (tid == 32) {
+    if (tid == 64) {
       const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
       if (a.tmax != nullptr) a.tmax[(size_t)s * ntiles + tpos] = tile_tmax;
       atomicAdd(&S->tile_visits, 1ull);
+      atomicAdd(&S->units_run, (unsigned long long)(reps * nlive));
       atomicAdd(&S->pulls, a.tile_pulls[tpos] * (unsigned long long)reps);
       if (any) atomicMax(&S->last_changed_round, round + 1);
     }
@@ -800,16 +838,16 @@ cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out2,
   return cudaGetLastError();
 }
 
-// one block per source: tt[start] = 0 and the 27 tiles around the start's tile go on list 0
+// one block per source: tt[start] = 0 and every tile within star reach of the start's tile goes on list 0
 __global__ void init_sources_kernel(const RelaxArgs a) {
   const int s = blockIdx.x;
   const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
   if (px < 0 || px >= a.g.nx || py < 0 || py >= a.g.ny || pz < 0 || pz >= a.g.nz) return;  // start owned by another slab
-  if (threadIdx.x == 31)
+  if (threadIdx.x == 63)
     a.tt[(size_t)s * a.g.vol + ((size_t)(px + AX) * a.g.py + (py + AY)) * a.g.pz + (pz + AZ)] = 0.0f;
-  if (threadIdx.x < 27) {
+  if (threadIdx.x < NMARK) {
     const int tid = threadIdx.x;
-    const int ux = px / TX + tid / 9 - 1, uy = py / TY + (tid / 3) % 3 - 1, uz = pz / TZ + tid % 3 - 1;
+    const int ux = px / TX + tid / 9 - XREACH, uy = py / TY + (tid / 3) % 3 - 1, uz = pz / TZ + tid % 3 - 1;
     if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
       const unsigned ntiles = a.g.ntx * a.g.nty * a.g.ntz;
       const unsigned pos = atomicAdd(&a.st->count[0], 1u);
@@ -849,7 +887,7 @@ __global__ void __launch_bounds__(256) merge_halo_kernel(const RelaxArgs a, cons
       *changed_flag = 1u;
       const int tx = c[0] / TX, ty = c[1] / TY, tz = c[2] / TZ;
       const unsigned bits = __float_as_uint(v);
-      for (int dx = -1; dx <= 1; ++dx)
+      for (int dx = -XREACH; dx <= XREACH; ++dx)
         for (int dy = -1; dy <= 1; ++dy)
           for (int dz = -1; dz <= 1; ++dz) {
             const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
@@ -903,14 +941,20 @@ int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed)
   return 0;
 }
 
-template <int RXY, typename STAR, int SPLIT = 1>
+// compute warps per CTA: the 3-FS star has too few columns to share out 16 ways; its small staged boxes
+// let three 5-warp CTAs share an SM instead
+template <int RXY>
+constexpr int warps_for() { return RXY == 2 ? 4 : MAX_WARPS; }
+
+template <int RXY, typename STAR>
 static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   using D = TileDims<RXY>;
-  const size_t smem = SPLIT == 1 ? D::SMEM : D::SMEM_SPLIT;
-  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int NW = warps_for<RXY>();
+  const size_t smem = D::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR, SPLIT>, TILE_THREADS * SPLIT, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR, NW>, 32 * NW, smem);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return e;
@@ -918,31 +962,19 @@ static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   out->rxy = RXY;
   out->grid = per_sm * sms;
   out->smem_bytes = smem;
-  out->split = SPLIT;
+  out->nw = NW;
   return cudaSuccess;
 }
-template <int R, typename STAR>
-static cudaError_t prepare_any(int split, int device, TiledLaunch* out) {
-  if constexpr (R == 7) {  // the split variant only exists where one CTA per SM is the limit
-    if (split == 2) return prepare_variant<R, STAR, 2>(device, out);
-  }
-  return prepare_variant<R, STAR, 1>(device, out);
+template <int RXY, typename STAR>
+static void launch_variant(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                           const RelaxArgs& a, cudaStream_t stream) {
+  constexpr int NW = warps_for<RXY>();
+  relax_tiled<RXY, STAR, NW><<<tl.grid, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
 }
-template <int R, typename STAR>
-static void launch_any(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt, const RelaxArgs& a,
-                       cudaStream_t stream) {
-  if constexpr (R == 7) {
-    if (tl.split == 2) {
-      relax_tiled<R, STAR, 2><<<tl.grid, 2 * TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
-      return;
-    }
-  }
-  relax_tiled<R, STAR, 1><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
-}
-cudaError_t tiled_prepare(int rxy, int stock_id, int split, int device, TiledLaunch* out) {
+cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
   out->stock_id = stock_id;
 #define SWEEPTT_STOCK_STAR(id, name, r, ...) \
-  if (stock_id == id) return prepare_any<r, Star_##name>(split, device, out);
+  if (stock_id == id) return prepare_variant<r, Star_##name>(device, out);
 #include "stock_stars.inc"
 #undef SWEEPTT_STOCK_STAR
   switch (rxy) {
@@ -955,17 +987,17 @@ cudaError_t tiled_prepare(int rxy, int stock_id, int split, int device, TiledLau
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
                                const RelaxArgs& a, cudaStream_t stream) {
-#define SWEEPTT_STOCK_STAR(id, name, r, ...)                   \
-  if (tl.stock_id == id) {                                     \
-    launch_any<r, Star_##name>(tl, tm_slow, tm_tt, a, stream); \
-    return cudaGetLastError();                                 \
+#define SWEEPTT_STOCK_STAR(id, name, r, ...)                       \
+  if (tl.stock_id == id) {                                         \
+    launch_variant<r, Star_##name>(tl, tm_slow, tm_tt, a, stream); \
+    return cudaGetLastError();                                     \
   }
 #include "stock_stars.inc"
 #undef SWEEPTT_STOCK_STAR
   switch (tl.rxy) {
-    case 2: relax_tiled<2, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
-    case 4: relax_tiled<4, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
-    case 7: relax_tiled<7, StarGeneric><<<tl.grid, TILE_THREADS, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a); break;
+    case 2: launch_variant<2, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
+    case 4: launch_variant<4, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
+    case 7: launch_variant<7, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -1107,7 +1139,7 @@ cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream
     e = launch_fill_tmax(a, stream);
     if (e != cudaSuccess) return e;
   }
-  init_sources_kernel<<<a.nsrc, 32, 0, stream>>>(a);
+  init_sources_kernel<<<a.nsrc, 64, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

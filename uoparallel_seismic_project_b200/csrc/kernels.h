@@ -10,7 +10,7 @@ namespace sweeptt {
 struct TiledLaunch {
   int rxy;                   // halo template: 2, 4 or 7
   int stock_id;              // 0 = generic runtime-mask kernel, else a stock-star instantiation
-  int split;                 // 1, or 2 = two thread groups share the star's columns (16 warps per SM)
+  int nw;                    // compute warps per CTA (the star's columns of a tile are shared out between them)
   int grid;                  // persistent CTAs
   size_t smem_bytes;
 };
@@ -20,13 +20,14 @@ int tiled_variant_for_radius(int r);
 // smem row/plane pitches of a variant (host needs them to precompute column offsets).
 void tiled_variant_dims(int rxy, int* sxd, int* syd, int* szd);
 // Occupancy-derived persistent grid + opt-in shared memory; returns cudaSuccess or an error.
-cudaError_t tiled_prepare(int rxy, int stock_id, int split, int device, TiledLaunch* out);
+cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out);
 // Stock-star instantiation whose compile-time pattern list equals `masks` (ascending), or 0.
 int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed);
 
 // Upload the column tables into __constant__ memory (stream ordered).
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, cudaStream_t stream);
+                                  const ExtraDev* extra, int nextra, const unsigned short* psplit, int npsplit,
+                                  cudaStream_t stream);
 
 struct RelaxArgs {
   BoxGeom g;
@@ -47,6 +48,7 @@ struct RelaxArgs {
   int ncols, nextra;
   int max_inner;               // in-tile relaxation passes per visit (>= 1)
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
+  int npat;                    // pattern groups (generic kernel; the stock kernels know theirs at compile time)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
 

@@ -164,6 +164,7 @@ struct sweeptt_ctx {
   bool maps_valid = false;
   int consts_rxy = -1;  // variant the __constant__ tables were built for
   std::vector<int> pat_begin;  // column ranges per k-pattern (stock-star kernels)
+  std::vector<unsigned short> psplit;  // per pattern group: first column of every fine part (kernels.cu c_psplit)
   std::vector<PullColumn> dev_columns;  // pattern-sorted, even-padded columns as uploaded
 
   cudaGraphExec_t graph_exec = nullptr;
@@ -505,31 +506,67 @@ static int choose_kernel(sweeptt_ctx* c) {
                    [](const PullColumn& a, const PullColumn& b) { return a.kmask < b.kmask; });
   std::vector<uint32_t> masks;
   c->pat_begin.clear();
-  {
-    // pad every pattern group to an even column count by repeating its last column (relaxing a
-    // column twice is harmless) -- the stock-star kernels process columns in ping-pong pairs
-    std::vector<PullColumn> padded;
-    size_t i = 0;
-    while (i < c->star.columns.size()) {
-      size_t j = i;
-      while (j < c->star.columns.size() && c->star.columns[j].kmask == c->star.columns[i].kmask) ++j;
+  for (size_t i = 0; i < c->star.columns.size(); ++i)
+    if (i == 0 || c->star.columns[i].kmask != c->star.columns[i - 1].kmask) {
       masks.push_back(c->star.columns[i].kmask);
-      c->pat_begin.push_back((int)padded.size());
-      padded.insert(padded.end(), c->star.columns.begin() + i, c->star.columns.begin() + j);
-      if ((j - i) & 1) padded.push_back(c->star.columns[j - 1]);
-      i = j;
+      c->pat_begin.push_back((int)i);
     }
-    c->pat_begin.push_back((int)padded.size());
-    c->dev_columns = padded;
-  }
+  c->pat_begin.push_back((int)c->star.columns.size());
+  c->dev_columns = c->star.columns;
   int stock = 0;
   if ((int)masks.size() <= MAX_PATTERNS && !getenv("SWEEPTT_GENERIC"))
     stock = tiled_stock_star_for(masks.data(), (int)masks.size(), rxy);
   const char* force = getenv("SWEEPTT_FORCE_RXY");  // testing: run a small star in a wider halo variant
   if (force && atoi(force) >= rxy) { rxy = tiled_variant_for_radius(atoi(force)); stock = 0; }
-  int split = 2;  // two thread groups per tile for the R=7 stock kernels (16 warps per SM): +2 % measured
-  if (const char* e = getenv("SWEEPTT_SPLIT")) split = atoi(e) == 2 ? 2 : 1;
-  CK(tiled_prepare(rxy, stock, (stock && rxy == 7) ? split : 1, c->device, &c->tl));
+  CK(tiled_prepare(rxy, stock, c->device, &c->tl));
+  {
+    // Share the star's columns out between the compute warps (kernels.cu, c_psplit): every column group
+    // is split between nw "fine parts"; a tile with nlive live units runs P = nw/nlive parts per unit,
+    // part p = fine parts [p*nlive, (p+1)*nlive).  Groups: the k-pattern groups for a stock-star kernel
+    // (one unrolled code block each), else plain chunks of the column list (the generic kernel reads every
+    // column's mask at run time).  Each column goes to the least loaded coarse part (pair of fine parts),
+    // then to the lighter half of it; a group's columns are then ordered by fine part.  Cost model of a
+    // column: its k offsets (packed math) + a constant for the window loads.  Fine parts 0/1 carry the
+    // owner's finishing work, booked as a head start.
+    const int nw = c->tl.nw;
+    const int ncols = (int)c->dev_columns.size();
+    std::vector<int> gbeg;
+    if (stock) {
+      gbeg = c->pat_begin;
+    } else {
+      const int per = std::max(nw, (ncols + MAX_PATTERNS - 1) / MAX_PATTERNS);
+      for (int i = 0; i < ncols; i += per) gbeg.push_back(i);
+      gbeg.push_back(ncols);
+      c->pat_begin = gbeg;
+    }
+    const int ngroups = (int)gbeg.size() - 1;
+    std::vector<double> load(nw, 0.0);
+    load[0] = 3.0;
+    if (nw > 1) load[1] = 3.0;
+    c->psplit.assign((size_t)MAX_PATTERNS * (MAX_WARPS + 1), 0);
+    std::vector<PullColumn> ordered;
+    ordered.reserve(ncols);
+    for (int g = 0; g < ngroups; ++g) {
+      std::vector<std::vector<PullColumn>> mine(nw);
+      for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) {
+        const double w = (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
+        int best = 0;
+        double bl = 1e300;
+        for (int cp = 0; cp < nw; cp += 2) {
+          const double l = load[cp] + (cp + 1 < nw ? load[cp + 1] : 0.0);
+          if (l < bl) { bl = l; best = cp; }
+        }
+        if (best + 1 < nw && load[best + 1] < load[best]) ++best;
+        mine[best].push_back(c->dev_columns[col]);
+        load[best] += w;
+      }
+      for (int f = 0; f <= MAX_WARPS; ++f) {
+        c->psplit[(size_t)g * (MAX_WARPS + 1) + f] = (unsigned short)ordered.size();
+        if (f < nw) ordered.insert(ordered.end(), mine[f].begin(), mine[f].end());
+      }
+    }
+    c->dev_columns = ordered;
+  }
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
   c->consts_rxy = -1;
@@ -578,6 +615,7 @@ static int upload_constants(sweeptt_ctx* c) {
   mix(cols.data(), cols.size() * sizeof(ColumnDev));
   mix(hd_packed.data(), hd_packed.size() * sizeof(float));
   mix(ex.data(), ex.size() * sizeof(ExtraDev));
+  mix(c->psplit.data(), c->psplit.size() * sizeof(unsigned short));
   auto sg = g_const_sig.find(c->device);
   if (sg != g_const_sig.end() && sg->second == sig && it != g_const_owner.end()) {
     g_const_owner[c->device] = c;
@@ -588,7 +626,7 @@ static int upload_constants(sweeptt_ctx* c) {
   // a different context may still be running with the old tables on another stream
   if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
   CK(upload_star_constants(cols.data(), (int)cols.size(), hd_packed.data(), (int)hd_packed.size(), ex.data(),
-                           (int)ex.size(), c->stream));
+                           (int)ex.size(), c->psplit.data(), (int)c->psplit.size(), c->stream));
   CK(cudaStreamSynchronize(c->stream));  // host vectors die here
   g_const_owner[c->device] = c;
   c->consts_rxy = c->tl.rxy;
@@ -716,6 +754,7 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.neg_zero = -0.0f;
   a.max_inner = c->max_inner;
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
+  a.npat = (int)c->pat_begin.size() - 1;
   return a;
 }
 
