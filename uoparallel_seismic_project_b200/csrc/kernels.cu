@@ -124,7 +124,8 @@ struct TileDims {
   static constexpr int BOX_FLOATS = SXD * SYD * SZD;
   // every staged box starts on a 128-byte boundary (TMA destination alignment)
   static constexpr int BOX_STRIDE = (BOX_FLOATS * 4 + 127) / 128 * 128 / 4;
-  static constexpr int ACC_WORDS = UNITS * KZ * 32;  // per-node min cells the star's parts are combined through
+  static constexpr int ACC_WORDS = 2 * UNITS * KZ * 32;  // per-node min cells the star's parts are combined through,
+                                                         // one set per ring stage (see relax_tiled)
   // 2 pipeline stages x (slowness box + travel-time box) + combine cells + alignment slack
   static constexpr size_t SMEM = sizeof(float) * (4 * BOX_STRIDE + ACC_WORDS) + 128;
 };
@@ -135,6 +136,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // named barriers over the compute warps only (the TMA producer warp never joins them)
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ int named_sync_or(int id, int nthreads, int pred) {
   int r;
@@ -391,8 +395,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   unsigned* s_acc = reinterpret_cast<unsigned*>(ring + 4 * D::BOX_STRIDE);
   __shared__ __align__(8) uint64_t full[2];
   __shared__ int s_tile[2];
-  __shared__ unsigned s_tmin[2];  // float bits of the smallest travel time the tile lowered
-  __shared__ unsigned s_tmax[2];  // float bits of the largest travel time of the tile's in-grid nodes
+  __shared__ unsigned s_tmin;  // float bits of the smallest travel time the tile lowered
+  __shared__ unsigned s_tmax;  // float bits of the largest travel time of the tile's in-grid nodes
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -400,8 +404,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1);
     fence_mbar_init();
-    s_tmin[0] = s_tmin[1] = 0x7f800000u;
-    s_tmax[0] = s_tmax[1] = 0u;
+    s_tmin = 0x7f800000u;
+    s_tmax = 0u;
   }
   for (int i = tid; i < D::ACC_WORDS; i += NCT) s_acc[i] = 0x7f800000u;
   __syncthreads();
@@ -438,6 +442,12 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
 
   // lane -> (x within the 4-wide unit, y): a quarter-warp shares x and spans 8 consecutive y, whose
   // rows are SZD = 28 floats apart -> conflict-free LDS.128.
+  // Synchronisation of a tile: every warp meets at ONE hardware barrier after its share of the columns
+  // (waiting there costs no issue slots; letting the parts run ahead into the next tile's mbarrier spin
+  // was measured slower).  Behind it only the unit owners go on with the tile (min cells -> pin -> stores
+  // -> neighbour activation) while the other parts already start the next tile, whose min cells are a
+  // second set.  With in-tile passes (small stars) every warp takes part in every step.
+  const bool multi = a.max_inner > 1;
   const int y = lane & 7;
   for (uint32_t it = 0;; ++it) {
     const int q = it & 1;
@@ -468,7 +478,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int b0 = ((x + RXY) * D::SYD + (y + RXY)) * SZD;
     const int gx = x0 + x, gy = y0 + y, gz = z0;
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
-    unsigned* cell = s_acc + (unit * KZ) * 32 + lane;  // cell[k * 32]
+    unsigned* cell = s_acc + ((q * UNITS + unit) * KZ) * 32 + lane;  // cell[k * 32]
     float vn[KZ], acc[KZ];
 #pragma unroll
     for (int j = 0; j < KZ / 4; ++j) {
@@ -546,8 +556,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
           if (acc[k] < bq[k]) { pass_changed = 1; lowered |= 1u << k; }
       }
       ++reps;
-      if (a.max_inner <= 1) break;  // one pass per visit
-      last_pass_changed = named_sync_or(2, NCT, pass_changed);  // also: every warp is done reading the staged box
+      if (!multi) break;  // one pass per visit
+      last_pass_changed = named_sync_or(3, NCT, pass_changed);  // also: every warp is done reading the staged box
       if (!last_pass_changed || reps >= a.max_inner) break;
       if (owner && pass_changed) {
 #pragma unroll
@@ -555,7 +565,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
           *reinterpret_cast<float4*>(st + b0 + ZHALO + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
       published = true;
-      named_sync(3, NCT);
+      named_sync(4, NCT);
       if (!owner) {  // the other parts restart from the published values
 #pragma unroll
         for (int j = 0; j < KZ / 4; ++j) {
@@ -564,6 +574,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         }
       }
     }
+
+    if (!multi && !owner) continue;  // this part's work on the tile is done
 
     const int changed = owner && lowered != 0;
     if (owner) {
@@ -588,44 +600,53 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       }
       const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmx));
       if (lane == 0) {
-        atomicMax(&s_tmax[q], wmax);
+        atomicMax(&s_tmax, wmax);
         if (wmin != 0x7f800000u) {
           atomicAdd(&S->units_changed, 1ull);
-          atomicMin(&s_tmin[q], wmin);
+          atomicMin(&s_tmin, wmin);
         }
       }
     }
-    if (tid == 0) {  // the other stage's cells: read by everyone before this tile's first barrier, used again after the next one
-      s_tmin[q ^ 1] = 0x7f800000u;
-      s_tmax[q ^ 1] = 0u;
+    // "anything changed in the tile": over every warp with in-tile passes (also the barrier that ends all
+    // reads of the staged boxes there), else over the unit owners only
+    int any;
+    if (multi) {
+      if (published) fence_proxy_async();  // generic-proxy writes to the stage precede the next TMA fill
+      any = named_sync_or(3, NCT, changed);
+    } else {
+      any = (nlive == 2) ? named_sync_or(5, 64, changed) : __any_sync(0xffffffffu, changed);
+      last_pass_changed = any;
     }
-    if (published) fence_proxy_async();  // generic-proxy writes to the stage precede the next TMA fill
-
-    // block-wide "anything changed" (also the barrier that ends all smem reads of this tile)
-    const int any = named_sync_or(2, NCT, changed);
-    if (a.max_inner <= 1) last_pass_changed = any;
-    const unsigned tile_tmin = s_tmin[q], tile_tmax = s_tmax[q];
-    if (any && tid < NMARK) {
+    if (wq != 0) continue;  // warp 0 (owner of unit 0) wakes the neighbours and keeps the books
+    const unsigned tile_tmin = s_tmin, tile_tmax = s_tmax;
+    __syncwarp();
+    if (lane == 0) {  // the next updates come from owners that first meet this warp at the next tile's barrier
+      s_tmin = 0x7f800000u;
+      s_tmax = 0u;
+    }
+    if (any) {
       // a changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected;
       // the tile itself only needs another visit if its last in-tile pass still changed something
-      const int dx = tid / 9 - XREACH, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
-      const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-      const bool self = (dx == 0 && dy == 0 && dz == 0);
-      bool reach = (abs(dx) - 1) * TX < RXY;  // x distance between the closest nodes of the two tiles
-      if (self && !last_pass_changed) reach = false;
-      if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
-        const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
-        // Downwind filter: every candidate that one of our lowered nodes can offer is
-        // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
-        // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
-        // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
-        bool useful = true;
-        if (a.tmax != nullptr && !self)
-          useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < a.tmax[u];
-        if (useful) atomicMin(&a.key[u], tile_tmin);
+      for (int m = lane; m < NMARK; m += 32) {
+        const int dx = m / 9 - XREACH, dy = (m / 3) % 3 - 1, dz = m % 3 - 1;
+        const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
+        const bool self = (dx == 0 && dy == 0 && dz == 0);
+        bool reach = (abs(dx) - 1) * TX < RXY;  // x distance between the closest nodes of the two tiles
+        if (self && !last_pass_changed) reach = false;
+        if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
+          const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
+          // Downwind filter: every candidate that one of our lowered nodes can offer is
+          // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
+          // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
+          // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
+          bool useful = true;
+          if (a.tmax != nullptr && !self)
+            useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < a.tmax[u];
+          if (useful) atomicMin(&a.key[u], tile_tmin);
+        }
       }
     }
-    if (tid == 64) {
+    if (lane == 31) {
       const int tpos = (tx * a.g.nty + ty) * a.g.ntz + tz;
       if (a.tmax != nullptr) a.tmax[(size_t)s * ntiles + tpos] = tile_tmax;
       atomicAdd(&S->tile_visits, 1ull);

@@ -321,22 +321,30 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   CK(cudaSetDevice(c->device));
   BoxGeom g{};
   {
-    // window axis (kernel z, tiled by TZ=32): the caller's z unless another axis wastes >25% fewer
-    // lanes.  (Measured on 241x241x51: windows along y raise lane efficiency 0.80 -> 0.94 but the
-    // coarser 32-long tiles along a long axis make the active-tile shell thicker: 61 ms vs 53 ms.)
+    // Axis order of the kernel: any permutation of the caller's axes gives the same field (the star is
+    // permuted with it); the kernel's granularity is 4 nodes along its x (a tile's 4-wide units are
+    // skipped individually), TY along y and TZ along z, so the order that wastes the fewest lanes in
+    // partly filled edge tiles wins (241x241x51: the 51 axis becomes kernel x, 52/51 instead of 56/51).
+    // Ties keep the caller's order.  SWEEPTT_WINDOW_AXIS=a forces caller axis a to be the window axis.
     const int n[3] = {nx, ny, nz};
-    int win = 2;
+    static const int perms[6][3] = {{0, 1, 2}, {1, 0, 2}, {0, 2, 1}, {2, 0, 1}, {1, 2, 0}, {2, 1, 0}};
+    const int gran[3] = {4, TY, TZ};
+    int pick = 0;
     double best = -1;
-    for (int a = 2; a >= 0; --a) {  // ties keep the caller's z (no permutation)
-      const double eff = (double)n[a] / (double)(((n[a] + TZ - 1) / TZ) * TZ);
-      if (eff > best * (a == 2 ? 1.0 : 1.25)) { best = eff; win = a; }
+    int forced = -1;
+    if (const char* e = getenv("SWEEPTT_WINDOW_AXIS")) forced = std::max(0, std::min(2, atoi(e)));
+    if (c->force_window_axis >= 0) forced = c->force_window_axis;
+    for (int pi = 0; pi < 6; ++pi) {
+      if (forced >= 0 && perms[pi][2] != forced) continue;
+      if (c->force_window_axis >= 0 && pi != 0) continue;  // slabs: the caller's order exactly
+      double eff = 1.0;
+      for (int q = 0; q < 3; ++q) {
+        const int len = n[perms[pi][q]];
+        eff *= (double)len / (double)(((len + gran[q] - 1) / gran[q]) * gran[q]);
+      }
+      if (eff > best * 1.02) { best = eff; pick = pi; }  // a permutation must pay for its transposing copies
     }
-    if (const char* e = getenv("SWEEPTT_WINDOW_AXIS")) win = std::max(0, std::min(2, atoi(e)));
-    if (c->force_window_axis >= 0) win = c->force_window_axis;
-    int q = 0;
-    for (int a = 0; a < 3; ++a)
-      if (a != win) g.perm[q++] = a;
-    g.perm[2] = win;
+    for (int q = 0; q < 3; ++q) g.perm[q] = perms[pick][q];
     const long long ds[3] = {(long long)ny * nz, (long long)nz, 1};
     for (int k = 0; k < 3; ++k) g.dstride[k] = ds[g.perm[k]];
     g.nx = n[g.perm[0]]; g.ny = n[g.perm[1]]; g.nz = n[g.perm[2]];
@@ -541,8 +549,10 @@ static int choose_kernel(sweeptt_ctx* c) {
     }
     const int ngroups = (int)gbeg.size() - 1;
     std::vector<double> load(nw, 0.0);
-    load[0] = 3.0;
-    if (nw > 1) load[1] = 3.0;
+    double head = 12.0;  // measured on config 3 (16 sources): 0 -> 54.4 ms, 5 -> 53.5, 8 -> 50.6, 11 -> 49.9, 14 -> 49.8, 18 -> 50.0
+    if (const char* e = getenv("SWEEPTT_OWNER_BIAS")) head = atof(e);
+    load[0] = head;
+    if (nw > 1) load[1] = head;
     c->psplit.assign((size_t)MAX_PATTERNS * (MAX_WARPS + 1), 0);
     std::vector<PullColumn> ordered;
     ordered.reserve(ncols);
