@@ -289,7 +289,7 @@ def run_ours(args):
                               "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                               "config": {"workload": WORKLOAD}, "converged_sources_per_s": tot["sources"] / tot["elapsed_ms"] * 1e3,
                               "clocks": clocks, "gpu_launches": tot["launches"], "e2e": None,
-                              "roofline": {"bound": "fp32-issue", "kernel": "relax_tiled<7, fs818>", "unit": "Tlane-op/s",
+                              "roofline": {"bound": "fp32-issue", "kernel": "relax_tiled<7, fs818>", "unit": "TFLOP/s",
                                            "achieved": 4 * k_relax / (k_ms * 1e-3) / 1e12, "peak": peak,
                                            "frac": 4 * k_relax / (k_ms * 1e-3) / 1e12 / peak}}), flush=True)
         if dist is not None:
@@ -336,7 +336,7 @@ def run_ours(args):
     lane_ops = 4 * k_relax / (k_ms * 1e-3) / 1e12               # Tlane-op/s of the relax kernel alone
     peak_ops = sms * 128 * sm_max * 1e6 / 1e12
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tile_bytes = 8 * 8 * 32 * 12                                # algorithmic bytes per tile visit
+    tile_bytes = 8 * 8 * 8 * 12                                 # algorithmic bytes per tile visit (8x8x8 nodes x 12 B)
     line = {
         "metric": "GRelax/s", "value": value, "unit": "GRelax/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot["elapsed_ms"] / args.steps, "higher_is_better": True,
@@ -355,11 +355,11 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(np.prod(DIMS)) * 4, "d2h_bytes_per_step": int(np.prod(DIMS)) * 4 * nsrc},
         "roofline": {
             "bound": "fp32-issue", "kernel": "relax_tiled<7, fs818>",
-            "achieved": lane_ops, "peak": peak_ops, "unit": "Tlane-op/s", "frac": lane_ops / peak_ops,
+            "achieved": lane_ops, "peak": peak_ops, "unit": "TFLOP/s", "frac": lane_ops / peak_ops,
             "frac_at_run_clock": lane_ops / (sms * 128 * sm_run * 1e6 / 1e12),
             "grelax_per_s_kernel": k_relax / (k_ms * 1e-3) / 1e9,
             "avg_launch_ms": k_ms / max(1, k_launch), "launches_measured": k_launch,
-            "peak_source": f"{sms} SMs x 128 lanes x {sm_max:.0f} MHz (clocks.max.sm), 4 lane-ops per pull "
+            "peak_source": f"{sms} SMs x 128 lanes x {sm_max:.0f} MHz (clocks.max.sm), 4 fp32 operations per pull "
                            "(FADD, FMUL, FADD, FMNMX; no FMA allowed by the bit-exactness contract)",
             "hbm": {"achieved": tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9
                     if k_ms else None, "peak": hbm_peak, "unit": "GB/s",

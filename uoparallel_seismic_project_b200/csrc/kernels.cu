@@ -992,8 +992,13 @@ static void launch_variant(const TiledLaunch& tl, const CUtensorMap& tm_slow, co
   constexpr int NW = warps_for<RXY>();
   relax_tiled<RXY, STAR, NW><<<tl.grid, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
 }
+__global__ void compact_fused(const RelaxArgs a, unsigned long long cond);
 cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
   out->stock_id = stock_id;
+  {  // the single-block compaction keeps its keys in (opt-in) dynamic shared memory; per device
+    cudaError_t e = cudaFuncSetAttribute(compact_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4);
+    if (e != cudaSuccess) return e;
+  }
 #define SWEEPTT_STOCK_STAR(id, name, r, ...) \
   if (stock_id == id) return prepare_variant<r, Star_##name>(device, out);
 #include "stock_stars.inc"
@@ -1028,9 +1033,10 @@ cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow
 // selected tiles by activation key (counting sort into 32 key bins), so the persistent relaxation
 // CTAs pop tiles in increasing travel-time order -- later tiles of a round then read what earlier
 // ones produced (Gauss-Seidel along the propagation direction) -- and a round is one launch shorter.
-constexpr int FUSED_MAX_KEYS = 65536;
+constexpr int FUSED_MAX_KEYS = 49152;  // cached in shared memory (192 KB)
 constexpr int FUSED_BINS = 32;
 __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigned long long cond) {
+  extern __shared__ unsigned s_keys[];  // the keys are read from global memory ONCE; the three passes run on this copy
   __shared__ unsigned s_min;
   __shared__ unsigned s_bin[FUSED_BINS + 1];
   SolveState* S = a.st;
@@ -1040,7 +1046,12 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
   if (threadIdx.x <= FUSED_BINS) s_bin[threadIdx.x] = 0;
   __syncthreads();
   unsigned m = 0x7f800000u;
-  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) m = min(m, a.key[i]);
+#pragma unroll 8
+  for (unsigned i = threadIdx.x; i < total; i += 1024) {
+    const unsigned k = a.key[i];
+    s_keys[i] = k;
+    m = min(m, k);
+  }
   m = __reduce_min_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(&s_min, m);
   __syncthreads();
@@ -1049,8 +1060,8 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
   const unsigned thr = all ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
   const float scale = all ? 0.f : (float)FUSED_BINS / a.bucket;
   // pass A: histogram of the selected tiles' key bins
-  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) {
-    const unsigned k = a.key[i];
+  for (unsigned i = threadIdx.x; i < total; i += 1024) {
+    const unsigned k = s_keys[i];
     if (k != 0x7f800000u && k <= thr) {
       const int b = min(FUSED_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
       atomicAdd(&s_bin[b + 1], 1u);
@@ -1064,8 +1075,8 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
   __syncthreads();
   // pass B: scatter in bin order, clear the keys
   unsigned* wl = a.worklist + (size_t)nxt * a.cap;
-  for (unsigned i = threadIdx.x; i < total; i += blockDim.x) {
-    const unsigned k = a.key[i];
+  for (unsigned i = threadIdx.x; i < total; i += 1024) {
+    const unsigned k = s_keys[i];
     if (k != 0x7f800000u && k <= thr) {
       const int b = min(FUSED_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
       wl[atomicAdd(&s_bin[b], 1u)] = i;
@@ -1092,7 +1103,7 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
 cudaError_t launch_compact(const RelaxArgs& a, unsigned long long cond, cudaStream_t stream) {
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
   if (total <= (size_t)FUSED_MAX_KEYS) {
-    compact_fused<<<1, 1024, 0, stream>>>(a, cond);
+    compact_fused<<<1, 1024, (total * 4 + 15) / 16 * 16, stream>>>(a, cond);
     return cudaGetLastError();
   }
   const unsigned blocks = (unsigned)((total + 255) / 256);

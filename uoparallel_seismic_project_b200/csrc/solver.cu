@@ -345,6 +345,9 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
       if (eff > best * 1.02) { best = eff; pick = pi; }  // a permutation must pay for its transposing copies
     }
     for (int q = 0; q < 3; ++q) g.perm[q] = perms[pick][q];
+    if (getenv("SWEEPTT_DEBUG"))
+      fprintf(stderr, "sweeptt: %d x %d x %d, kernel axes = caller axes (%d,%d,%d), lane efficiency %.3f\n", nx, ny, nz,
+              g.perm[0], g.perm[1], g.perm[2], best);
     const long long ds[3] = {(long long)ny * nz, (long long)nz, 1};
     for (int k = 0; k < 3; ++k) g.dstride[k] = ds[g.perm[k]];
     g.nx = n[g.perm[0]]; g.ny = n[g.perm[1]]; g.nz = n[g.perm[2]];
@@ -498,8 +501,7 @@ extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsiz
 static int choose_kernel(sweeptt_ctx* c) {
   const int want = c->opts.kernel;
   int rxy = 0;
-  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() + MAX_PATTERNS + 2 <= MAX_COLUMNS && 2 * (int)c->star.col_hd.size() <= MAX_COL_HD &&
-                    (int)c->star.col_hd.size() <= MAX_COL_HD && (int)c->star.extra.size() <= MAX_EXTRA;
+  const bool fits = c->star.fits_tiled() && (int)c->star.columns.size() + MAX_PATTERNS + 2 <= MAX_COLUMNS && (int)c->star.col_hd.size() <= MAX_COL_HD && (int)c->star.extra.size() <= MAX_EXTRA;
   if (fits) rxy = tiled_variant_for_radius(std::max(c->star.rx, c->star.ry));
   if (want == SWEEPTT_KERNEL_SIMPLE || (want == SWEEPTT_KERNEL_AUTO && rxy == 0)) {
     c->kernel_used = SWEEPTT_KERNEL_SIMPLE;
