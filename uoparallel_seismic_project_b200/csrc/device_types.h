@@ -61,6 +61,13 @@ struct SolveState {
   int max_rounds;            // 0 = unlimited; the graph WHILE loop stops here
   unsigned kmin_bits;        // smallest activation key among dirty tiles (scan pass of the compaction)
   int pad;
+  // ---- single-launch (persistent) scheduling: work lists come in GENERATIONS built on the device ----
+  unsigned gen;              // newest published generation; its list is work list (gen & 1)
+  unsigned builder;          // generation some CTA has claimed to build (== gen + 1 while a build is running)
+  unsigned done;             // 1 = fixed point reached, 2 = watchdog gave up (error)
+  unsigned inflight;         // tiles published on a list and not yet finished
+  unsigned gcount[4];        // entries of generation g's list, at [g & 3]
+  unsigned gcursor[4];       // pop cursor of generation g, at [g & 3]
 };
 
 struct ColumnDev {

@@ -43,11 +43,12 @@ namespace sweeptt {
 __constant__ ColumnDev c_cols[MAX_COLUMNS];
 __constant__ float c_col_hd[MAX_COL_HD];
 __constant__ ExtraDev c_extra[MAX_EXTRA];
-// c_psplit[g * (MAX_WARPS + 1) + f]: first column of fine part f (of nw) within pattern group g; part p of
-// P = nw / nlive parts runs the columns [c_psplit[g][p * nlive], c_psplit[g][(p + 1) * nlive]) of EVERY group,
-// so all warps walk the pattern code blocks in the same order (instruction-cache locality) and the host
-// can balance the parts' total cost
-__constant__ unsigned short c_psplit[MAX_PATTERNS * (MAX_WARPS + 1)];
+// c_psplit[(t * MAX_PATTERNS + g) * (MAX_WARPS + 1) + p]: first column of part p within column group g; part p
+// runs the columns [c_psplit[..][p], c_psplit[..][p + 1]) of EVERY group, so all warps walk the pattern code
+// blocks in the same order (instruction-cache locality) and the host can balance the parts' total cost.
+// Table t = 0: one live unit shared by all nw warps; t = 1, 2: units 0 and 1 of a tile with two live units;
+// t = 3..5: the same for the single-launch kernels (their finisher warp needs a longer head start).
+__constant__ unsigned short c_psplit[6 * MAX_PATTERNS * (MAX_WARPS + 1)];
 
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
                                   const ExtraDev* extra, int nextra, const unsigned short* psplit, int npsplit,
@@ -328,10 +329,10 @@ __device__ __forceinline__ void run_pattern_range(const float* __restrict__ sv, 
   }
 }
 
-// `f0`,`f1`: this warp's fine-part range; `after(g)` runs after pattern group g-1 (the ring feeder's hooks)
+// `f0`: index of this warp's first cut point of group 0 in c_psplit; `after(g)` runs after pattern group g-1 (the ring feeder's hooks)
 template <typename HOOK, uint32_t... M>
 __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
-                                              const float* __restrict__ st, int b0, const RelaxArgs& a, int f0, int f1,
+                                              const float* __restrict__ st, int b0, const RelaxArgs& a, int f0,
                                               const float (&vn)[KZ], float (&acc)[KZ], HOOK&& after) {
   u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
 #pragma unroll
@@ -345,7 +346,7 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
 #pragma unroll
     for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
     for (int g = 0; g < a.npat; ++g) {
-      const int lo = c_psplit[g * (MAX_WARPS + 1) + f0], hi_ = c_psplit[g * (MAX_WARPS + 1) + f1];
+      const int lo = c_psplit[g * (MAX_WARPS + 1) + f0], hi_ = c_psplit[g * (MAX_WARPS + 1) + f0 + 1];
       for (int c = lo; c < hi_; ++c) {
         const ColumnDev col = c_cols[c];
         const float* pv = sv + b0 + col.soff;
@@ -367,9 +368,112 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
   } else {
     int g = 0;
     ((run_pattern_range<M>(sv, st, b0, a.pat_begin[g], c_psplit[g * (MAX_WARPS + 1) + f0],
-                           c_psplit[g * (MAX_WARPS + 1) + f1], vn, vnE, vnO, nz2, acc),
+                           c_psplit[g * (MAX_WARPS + 1) + f0 + 1], vn, vnE, vnO, nz2, acc),
       ++g, after(g, (int)sizeof...(M))),
      ...);
+  }
+}
+
+// ---- single-launch scheduling helpers -----------------------------------------------------------
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+__device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+constexpr int GEN_BINS = 32;
+constexpr int TILE_NONE = -1;     // staged instead of a tile: the solve is finished
+constexpr int TILE_NEXT_GEN = -2; // staged instead of a tile: this generation's list is handed out
+constexpr int TILE_BUILD = -3;    // staged instead of a tile: this CTA popped the list's trigger entry and builds the
+                                  // next generation EARLY, while the other CTAs are still busy with the rest of the list
+
+// Build generation `g_new` from the activation keys (the device-side counterpart of compact_fused, run by
+// ONE CTA while the others keep relaxing): smallest pending key -> bucket threshold -> counting sort of the
+// selected tiles by key into work list (g_new & 1).  Tiles that are still on a list or being relaxed
+// (busy) are left for a later generation, so a tile is never relaxed by two CTAs at once.  `cache` is the
+// CTA's idle TMA ring.  Nothing pending and nothing in flight = fixed point.
+template <int NCT>
+__device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* cache, bool early) {
+  __shared__ unsigned s_min, s_inflight, s_stop;
+  __shared__ unsigned s_bin[GEN_BINS + 1];
+  SolveState* S = a.st;
+  const int tid = threadIdx.x;
+  const unsigned total = (unsigned)((size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz);
+  unsigned* wl = a.worklist + (size_t)(g_new & 3u) * a.cap;
+  for (unsigned spins = 0;; ++spins) {
+    if (tid == 0) {
+      s_inflight = atomicAdd(&S->inflight, 0u);  // BEFORE the scan: 0 here means nobody can still add a key
+      s_min = 0x7f800000u;
+      s_stop = 0u;
+    }
+    if (tid <= GEN_BINS) s_bin[tid] = 0;
+    __syncthreads();
+    const unsigned inflight_before = s_inflight;
+    unsigned m = 0x7f800000u;
+#pragma unroll 16
+    for (unsigned i = tid; i < total; i += NCT) {
+      unsigned k = __ldcg(&a.key[i]);
+      // a busy tile stays pending in global memory -- unless nothing is in flight, in which case the flag is
+      // only the not-yet-visible tail of a finished tile (the finish path does not fence for it)
+      if (k != 0x7f800000u && inflight_before != 0u && __ldcg(&a.busy[i]) != 0u) k = 0x7f800000u;
+      cache[i] = k;
+      m = min(m, k);
+    }
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((tid & 31) == 0 && m != 0x7f800000u) atomicMin(&s_min, m);
+    __syncthreads();
+    const float kmin = __uint_as_float(s_min);
+    const bool all = a.bucket < 0.f;
+    const unsigned thr = all ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
+    const float scale = a.bin_scale;  // GEN_BINS / bucket, divided on the host (a division here would put FFMAs into
+                                      // this kernel's SASS, which tests/test_sass.py keeps free of them)
+    for (unsigned i = tid; i < total; i += NCT) {
+      const unsigned k = cache[i];
+      if (k != 0x7f800000u && k <= thr) {
+        const int b = min(GEN_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
+        atomicAdd(&s_bin[b + 1], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int b = 0; b < GEN_BINS; ++b) s_bin[b + 1] += s_bin[b];
+    __syncthreads();
+    const unsigned cnt = s_bin[GEN_BINS];
+    __syncthreads();
+    for (unsigned i = tid; i < total; i += NCT) {
+      const unsigned k = cache[i];
+      if (k != 0x7f800000u && k <= thr) {
+        const int b = min(GEN_BINS - 1, (int)((__uint_as_float(k) - kmin) * scale));
+        wl[atomicAdd(&s_bin[b], 1u)] = i;
+        a.key[i] = 0x7f800000u;
+        a.busy[i] = 1u;
+      }
+    }
+    __threadfence();  // list entries, key and busy updates are visible before the generation is
+    __syncthreads();
+    if (tid == 0) {
+      if (cnt != 0) {
+        S->gcount[g_new & 3u] = cnt;
+        S->gcursor[g_new & 3u] = 0u;
+        atomicAdd(&S->inflight, cnt);
+        S->round += 1;
+        __threadfence();
+        st_volatile_u32(&S->gen, g_new);
+        s_stop = 1u;
+      } else if (early) {
+        st_volatile_u32(&S->builder, g_new - 1u);  // nothing to hand out yet: give the claim back
+        s_stop = 1u;
+      } else if (s_inflight == 0u) {
+        st_volatile_u32(&S->done, 1u);  // fixed point
+        s_stop = 1u;
+      } else if (spins > (1u << 22)) {
+        st_volatile_u32(&S->done, 2u);  // watchdog: tiles in flight never finished
+        s_stop = 1u;
+      } else {
+        __nanosleep(200);  // the tiles in flight will either wake something up or finish
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
   }
 }
 
@@ -384,17 +488,23 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
 //             KZ accumulators in registers, lowers the unit's per-node min cells in shared memory
 //             (atomicMin on the float bits: travel times are >= 0) and part 0 of the unit (the owner)
 //             finishes: start-point pin, changed test, 128-bit stores, activation of the neighbours.
-template <int RXY, typename STAR, int NW>
+template <int RXY, typename STAR, int NW, bool PERSIST>
 __global__ void __launch_bounds__(32 * NW, (RXY == 2) ? 3 : 1)
 relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
             const __grid_constant__ RelaxArgs a) {
   using D = TileDims<RXY>;
   constexpr int NCT = 32 * NW;
+  // warps with a second duty (the host gives them fewer columns, solver.cu): the unit owners (part 0 of a
+  // unit) finish the tile's arithmetic; thread FEED_TID drives the TMA ring; warp FIN_WARP wakes the
+  // neighbours and keeps the books
+  constexpr int FEED_TID = 32 * (NW / 2 - 1), FIN_WARP = NW - 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
   unsigned* s_acc = reinterpret_cast<unsigned*>(ring + 4 * D::BOX_STRIDE);
   __shared__ __align__(8) uint64_t full[2];
   __shared__ int s_tile[2];
+  __shared__ unsigned s_gen;   // PERSIST: the generation this CTA is popping from
+  __shared__ int s_role;
   __shared__ unsigned s_tmin;  // float bits of the smallest travel time the tile lowered
   __shared__ unsigned s_tmax;  // float bits of the largest travel time of the tile's in-grid nodes
 
@@ -406,6 +516,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     fence_mbar_init();
     s_tmin = 0x7f800000u;
     s_tmax = 0u;
+    s_gen = 0u;
   }
   for (int i = tid; i < D::ACC_WORDS; i += NCT) s_acc[i] = 0x7f800000u;
   __syncthreads();
@@ -424,6 +535,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       mbar_arrive(&full[q]);
       return;
     }
+    if constexpr (PERSIST) fence_proxy_async_global();  // other CTAs' stores of THIS launch (generic proxy) -> our TMA reads
     const int s = tile / ntiles;
     int tp = tile - s * ntiles;
     const int tz = tp % a.g.ntz; tp /= a.g.ntz;
@@ -435,10 +547,25 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY);
     tma_load_4d(sv + D::BOX_STRIDE, &tm_tt, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY, s);
   };
-  if (tid == 0) {
-    const unsigned i = atomicAdd(&S->cursor, 1u);
-    stage_tile(0, (i < cnt) ? (int)wl[i] : -1);
-  }
+  // synchronous pop (prologue, and after a generation switch): next tile id or a marker; thread 0 only
+  auto pop_now = [&]() -> int {
+    if constexpr (PERSIST) {
+      // generations are consumed IN ORDER: a list that was published early must not make anybody leave
+      // the rest of the one before it (its tiles would stay busy for ever)
+      for (;;) {
+        if (ld_volatile_u32(&S->done)) return TILE_NONE;
+        const unsigned g = s_gen;
+        const unsigned i = atomicAdd(&S->gcursor[g & 3u], 1u);
+        if (i < ld_volatile_u32(&S->gcount[g & 3u])) return (int)__ldcg(&a.worklist[(size_t)(g & 3u) * a.cap + i]);
+        if (ld_volatile_u32(&S->gen) == g) return TILE_NEXT_GEN;
+        s_gen = g + 1u;
+      }
+    } else {
+      const unsigned i = atomicAdd(&S->cursor, 1u);
+      return (i < cnt) ? (int)wl[i] : TILE_NONE;
+    }
+  };
+  if (tid == 0) stage_tile(0, pop_now());
 
   // lane -> (x within the 4-wide unit, y): a quarter-warp shares x and spans 8 consecutive y, whose
   // rows are SZD = 28 floats apart -> conflict-free LDS.128.
@@ -449,15 +576,66 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   // second set.  With in-tile passes (small stars) every warp takes part in every step.
   const bool multi = a.max_inner > 1;
   const int y = lane & 7;
+  bool build_next = false;
   for (uint32_t it = 0;; ++it) {
     const int q = it & 1;
     mbar_wait(&full[q], (it >> 1) & 1);
     const int tile = s_tile[q];
-    if (tile < 0) break;
-    // stage q^1 is free (every warp is past the last barrier of the previous tile): claim the next tile
-    unsigned pop_i = 0;
-    int next_tile = -1;
-    if (tid == 0) pop_i = atomicAdd(&S->cursor, 1u);
+    if (tile == TILE_NONE) break;
+    if constexpr (PERSIST) {
+      if (tile == TILE_NEXT_GEN || tile == TILE_BUILD) {
+        // TILE_NEXT_GEN: the list of generation s_gen is handed out.  The first CTA to get here builds the
+        // next one from the activation keys; CTAs arriving during the build wait for it; later ones find it
+        // published.  TILE_BUILD: this CTA builds the next generation ahead of time (nobody waits for it).
+        const bool early = tile == TILE_BUILD;
+        __syncthreads();  // every warp is done with the previous tile (the ring is idle: it is the build's cache)
+        for (;;) {
+          if (tid == 0) {
+            const unsigned g = s_gen;  // the generation this CTA is in: only its successor is ours to build
+            int role = 0;                                                      // 0: nothing to do here
+            if (ld_volatile_u32(&S->done)) role = 0;
+            else if (ld_volatile_u32(&S->gen) != g) role = 0;                   //    (a newer list is there)
+            else if (atomicCAS(&S->builder, g, g + 1u) == g) role = 2;          // 2: build it
+            else role = early ? 0 : 1;                                          // 1: wait for the builder
+            s_role = role;
+          }
+          __syncthreads();
+          const int role = s_role;
+          __syncthreads();
+          if (role == 2) {
+            build_generation<NCT>(a, s_gen + 1u, reinterpret_cast<unsigned*>(ring), early);
+            fence_proxy_async_all();  // the ring was written through the generic proxy; TMA fills it next
+            __syncthreads();
+            break;
+          }
+          if (role == 0) break;
+          if (tid == 0) {
+            // wait for the builder; an EARLY builder may give its claim back (nothing to hand out yet), then
+            // somebody who is out of work -- us -- has to build
+            unsigned spins = 0;
+            while (ld_volatile_u32(&S->gen) == s_gen && !ld_volatile_u32(&S->done) &&
+                   ld_volatile_u32(&S->builder) != s_gen) {
+              __nanosleep(100);
+              if (++spins > (1u << 24)) { st_volatile_u32(&S->done, 2u); break; }
+            }
+          }
+          __syncthreads();
+        }
+        if (tid == 0) stage_tile(q ^ 1, pop_now());
+        continue;
+      }
+    }
+    // stage q^1 is free (every warp is past the last barrier of the previous tile): claim the next tile.
+    // Thread 0 does it in steps spread over its column phase, each consuming what the previous one asked
+    // for, so that no atomic, load or copy is ever waited for.
+    unsigned pop_i = 0, pop_g = 0, pop_c = 0;
+    int next_tile = TILE_NONE;
+    const bool build_now = build_next;  // (feeder thread) the tile staged last time was the list's trigger entry
+    build_next = false;
+    if (tid == FEED_TID) {
+      if constexpr (PERSIST) pop_g = s_gen;
+      else pop_i = atomicAdd(&S->cursor, 1u);
+    }
     const int s = tile / ntiles;
     int tp = tile - s * ntiles;
     const int tz = tp % a.g.ntz; tp /= a.g.ntz;
@@ -471,7 +649,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int nlive = (UNITS == 2 && x0 + 4 < a.g.nx) ? 2 : 1;
     const int P = NW / nlive;
     const int unit = wq / P, part = wq - unit * P;
-    const int f0 = part * nlive, f1 = f0 + nlive;  // fine-part range in c_psplit
+    const int f0 = (((PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * (MAX_WARPS + 1) + part;  // c_psplit index, group 0
     const bool owner = part == 0;
     const int x = (unit << 2) | (lane >> 3);
     // smem float index of this thread's window start for the (0,0) column
@@ -502,12 +680,38 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       // Thread 0 feeds the ring from two points of its first pass: the work-list entry is read a few
       // pattern groups after the atomic was issued, the copy starts a few groups later -- neither the
       // atomic nor the load nor the copy is ever waited for.
-      const bool feeds = (tid == 0 && reps == 0);
-      columns_phase(STAR{}, sv, st, b0, a, f0, f1, vn, acc, [&](int g, int npat) {
-        const int h0 = (npat + 5) / 6, h1 = (npat + 2) / 3;
+      const bool feeds = (tid == FEED_TID && reps == 0);
+      columns_phase(STAR{}, sv, st, b0, a, f0, vn, acc, [&](int g, int npat) {
+        const int h0 = (npat + 5) / 6, h1 = (npat + 2) / 3, h2 = (npat + 1) / 2;
         if (feeds) {
-          if (g == h0) next_tile = (pop_i < cnt) ? (int)wl[pop_i] : -1;
-          if (g == h1) stage_tile(q ^ 1, next_tile);
+          if constexpr (PERSIST) {
+            if (build_now) {
+              if (g == h2) stage_tile(q ^ 1, TILE_BUILD);
+            } else {
+            if (g == h0) {
+              pop_i = atomicAdd(&S->gcursor[pop_g & 3u], 1u);
+              pop_c = ld_volatile_u32(&S->gcount[pop_g & 3u]);
+            }
+            if (g == h1) {
+              // the entry `lookahead` before the list's end is the trigger: whoever pops it builds the next
+              // generation right after that tile, so that the new list is out when this one runs dry
+              if (a.lookahead != 0u && pop_c > 2u * a.lookahead && pop_i + a.lookahead == pop_c) build_next = true;
+              if (pop_i >= pop_c && ld_volatile_u32(&S->gen) != pop_g) {
+                // this generation is handed out and the next one is already published: take the next tile
+                // from it right here (the CTA then never leaves its pipeline); else the CTA goes to the switch
+                pop_g += 1u;
+                s_gen = pop_g;
+                pop_i = atomicAdd(&S->gcursor[pop_g & 3u], 1u);
+                pop_c = ld_volatile_u32(&S->gcount[pop_g & 3u]);
+              }
+              next_tile = (pop_i < pop_c) ? (int)__ldcg(&a.worklist[(size_t)(pop_g & 3u) * a.cap + pop_i]) : TILE_NEXT_GEN;
+            }
+            if (g == h2) stage_tile(q ^ 1, next_tile);
+            }
+          } else {
+            if (g == h0) next_tile = (pop_i < cnt) ? (int)wl[pop_i] : TILE_NONE;
+            if (g == h1) stage_tile(q ^ 1, next_tile);
+          }
         }
       });
       float bq[KZ];
@@ -575,7 +779,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       }
     }
 
-    if (!multi && !owner) continue;  // this part's work on the tile is done
+    const bool finisher = wq == FIN_WARP;
+    if (!multi && !owner && !finisher) continue;  // this part's work on the tile is done
 
     const int changed = owner && lowered != 0;
     if (owner) {
@@ -607,24 +812,31 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         }
       }
     }
-    // "anything changed in the tile": over every warp with in-tile passes (also the barrier that ends all
-    // reads of the staged boxes there), else over the unit owners only
-    int any;
+    // Hand-over to the finisher warp: with in-tile passes every warp meets once more (also the barrier that
+    // ends all reads of the staged boxes there); else the owners only ARRIVE at the finisher's barrier and
+    // go straight on to the next tile.
     if (multi) {
       if (published) fence_proxy_async();  // generic-proxy writes to the stage precede the next TMA fill
-      any = named_sync_or(3, NCT, changed);
+      (void)named_sync_or(3, NCT, changed);
+      if (!finisher) continue;
+    } else if (owner) {
+      named_arrive(5, 32 * (nlive + 1));
+      continue;
     } else {
-      any = (nlive == 2) ? named_sync_or(5, 64, changed) : __any_sync(0xffffffffu, changed);
-      last_pass_changed = any;
+      named_sync(5, 32 * (nlive + 1));
     }
-    if (wq != 0) continue;  // warp 0 (owner of unit 0) wakes the neighbours and keeps the books
     const unsigned tile_tmin = s_tmin, tile_tmax = s_tmax;
+    const int any = tile_tmin != 0x7f800000u;
+    if (!multi) last_pass_changed = any;
     __syncwarp();
     if (lane == 0) {  // the next updates come from owners that first meet this warp at the next tile's barrier
       s_tmin = 0x7f800000u;
       s_tmax = 0u;
     }
     if (any) {
+      // single launch: the owners' stores (ordered before this point by the owners' barrier) must be visible
+      // device-wide before any neighbour is woken up
+      if constexpr (PERSIST) __threadfence();
       // a changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected;
       // the tile itself only needs another visit if its last in-tile pass still changed something
       for (int m = lane; m < NMARK; m += 32) {
@@ -653,6 +865,16 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       atomicAdd(&S->units_run, (unsigned long long)(reps * nlive));
       atomicAdd(&S->pulls, a.tile_pulls[tpos] * (unsigned long long)reps);
       if (any) atomicMax(&S->last_changed_round, round + 1);
+    }
+    if constexpr (PERSIST) {
+      // the tile is finished: it may go on a list again, and the in-flight count drops (after the
+      // neighbour keys were set, so "nothing pending and nothing in flight" is never seen too early)
+      __syncwarp();
+      if (lane == 0) {
+        st_volatile_u32(&a.busy[tile], 0u);
+        if (any) __threadfence();  // the neighbours' keys are set before the count can reach zero
+        atomicSub(&S->inflight, 1u);
+      }
     }
   }
 }
@@ -972,25 +1194,33 @@ static cudaError_t prepare_variant(int device, TiledLaunch* out) {
   using D = TileDims<RXY>;
   constexpr int NW = warps_for<RXY>();
   const size_t smem = D::SMEM;
-  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int per_sm = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR, NW>, 32 * NW, smem);
+  e = cudaFuncSetAttribute(relax_tiled<RXY, STAR, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0, per_sm_p = 0, sms = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_tiled<RXY, STAR, NW, false>, 32 * NW, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, relax_tiled<RXY, STAR, NW, true>, 32 * NW, smem);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  if (per_sm < 1 || per_sm_p < 1) return cudaErrorLaunchOutOfResources;
   out->rxy = RXY;
   out->grid = per_sm * sms;
+  out->grid_persistent = per_sm_p * sms;
   out->smem_bytes = smem;
   out->nw = NW;
   return cudaSuccess;
 }
 template <int RXY, typename STAR>
 static void launch_variant(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
-                           const RelaxArgs& a, cudaStream_t stream) {
+                           const RelaxArgs& a, bool persistent, cudaStream_t stream) {
   constexpr int NW = warps_for<RXY>();
-  relax_tiled<RXY, STAR, NW><<<tl.grid, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+  if (persistent)
+    relax_tiled<RXY, STAR, NW, true><<<tl.grid_persistent, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+  else
+    relax_tiled<RXY, STAR, NW, false><<<tl.grid, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
 }
 __global__ void compact_fused(const RelaxArgs a, unsigned long long cond);
 cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
@@ -1011,21 +1241,55 @@ cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
-                               const RelaxArgs& a, cudaStream_t stream) {
-#define SWEEPTT_STOCK_STAR(id, name, r, ...)                       \
-  if (tl.stock_id == id) {                                         \
-    launch_variant<r, Star_##name>(tl, tm_slow, tm_tt, a, stream); \
-    return cudaGetLastError();                                     \
+static cudaError_t launch_relax_any(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                                    const RelaxArgs& a, bool persistent, cudaStream_t stream) {
+#define SWEEPTT_STOCK_STAR(id, name, r, ...)                                   \
+  if (tl.stock_id == id) {                                                     \
+    launch_variant<r, Star_##name>(tl, tm_slow, tm_tt, a, persistent, stream); \
+    return cudaGetLastError();                                                 \
   }
 #include "stock_stars.inc"
 #undef SWEEPTT_STOCK_STAR
   switch (tl.rxy) {
-    case 2: launch_variant<2, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
-    case 4: launch_variant<4, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
-    case 7: launch_variant<7, StarGeneric>(tl, tm_slow, tm_tt, a, stream); break;
+    case 2: launch_variant<2, StarGeneric>(tl, tm_slow, tm_tt, a, persistent, stream); break;
+    case 4: launch_variant<4, StarGeneric>(tl, tm_slow, tm_tt, a, persistent, stream); break;
+    case 7: launch_variant<7, StarGeneric>(tl, tm_slow, tm_tt, a, persistent, stream); break;
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                               const RelaxArgs& a, cudaStream_t stream) {
+  return launch_relax_any(tl, tm_slow, tm_tt, a, false, stream);
+}
+cudaError_t launch_relax_persistent(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                                    const RelaxArgs& a, cudaStream_t stream) {
+  return launch_relax_any(tl, tm_slow, tm_tt, a, true, stream);
+}
+size_t tiled_persistent_max_keys(int rxy) {  // the generation builder caches every key in the idle TMA ring
+  switch (rxy) {
+    case 2: return 4 * (size_t)TileDims<2>::BOX_STRIDE;
+    case 4: return 4 * (size_t)TileDims<4>::BOX_STRIDE;
+    case 7: return 4 * (size_t)TileDims<7>::BOX_STRIDE;
+  }
+  return 0;
+}
+// generation 0 = the list init_sources_kernel wrote: book its tiles as busy / in flight
+__global__ void persist_begin_kernel(const RelaxArgs a) {
+  SolveState* S = a.st;
+  const unsigned cnt = S->count[0];
+  for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) a.busy[a.worklist[i]] = 1u;
+  if (threadIdx.x == 0) {
+    S->gen = 0u; S->builder = 0u; S->done = 0u;
+    S->inflight = cnt;
+    S->gcount[0] = cnt; S->gcursor[0] = 0u;
+  }
+}
+cudaError_t launch_persist_begin(const RelaxArgs& a, cudaStream_t stream) {
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  cudaError_t e = cudaMemsetAsync(a.busy, 0, total * sizeof(unsigned), stream);
+  if (e != cudaSuccess) return e;
+  persist_begin_kernel<<<1, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

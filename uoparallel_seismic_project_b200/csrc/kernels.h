@@ -12,6 +12,7 @@ struct TiledLaunch {
   int stock_id;              // 0 = generic runtime-mask kernel, else a stock-star instantiation
   int nw;                    // compute warps per CTA (the star's columns of a tile are shared out between them)
   int grid;                  // persistent CTAs
+  int grid_persistent;       // ... of the single-launch variant
   size_t smem_bytes;
 };
 
@@ -36,24 +37,36 @@ struct RelaxArgs {
   int nsrc;
   const int* src_xyz;          // 3 ints per source (logical coords)
   SolveState* st;
-  unsigned* worklist;          // 2 * cap entries
+  unsigned* worklist;          // 4 * cap entries: one list per generation in flight (round-based scheduling uses two)
   unsigned cap;
   unsigned* key;               // nsrc * ntiles activation keys: float bits of the smallest travel time
                                // that changed next to the tile since it was last relaxed; INF = clean
   unsigned* tmax;              // nsrc * ntiles: float bits of an upper bound of each tile's largest in-grid travel
                                // time (INF until the tile was relaxed with every node reached); nullptr = no filter
   float dmin;                  // lower bound (>= 0) of every edge delay fl(hd*fl(v_n+v_m)) of this model and star
+  unsigned* busy;              // nsrc * ntiles: 1 while a tile is on a published list or being relaxed (single-launch
+                               // scheduling only: such a tile is never put on a second list)
+  float bin_scale;             // 32 / bucket (0 when bucket < 0): key -> sort bin of the generation builder
   float bucket;                // only tiles with key <= (smallest key) + bucket run in a round; <0 = all
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
   int ncols, nextra;
   int max_inner;               // in-tile relaxation passes per visit (>= 1)
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
+  unsigned lookahead;          // single launch: the list entry this far before the end triggers the next build
   int npat;                    // pattern groups (generic kernel; the stock kernels know theirs at compile time)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
 
 cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow,
                                const CUtensorMap& tm_tt, const RelaxArgs& a, cudaStream_t stream);
+// Single-launch solve: ONE persistent launch relaxes to the fixed point; the CTAs build the next work
+// list ("generation") themselves as soon as the current one is handed out, so there is no round barrier,
+// no per-round launch and no tail.  Needs every key of the problem to fit the kernel's shared memory
+// (tiled_persistent_max_keys) and launch_reset + launch_persist_begin on the same stream before it.
+cudaError_t launch_relax_persistent(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
+                                    const RelaxArgs& a, cudaStream_t stream);
+cudaError_t launch_persist_begin(const RelaxArgs& a, cudaStream_t stream);
+size_t tiled_persistent_max_keys(int rxy);
 // Two launches: (1) min-reduce the activation keys, (2) move every tile whose key is within the
 // bucket of that minimum to the next work list (clearing its key), flip parity, advance the
 // round and (when cond != 0) set the CUDA-graph WHILE condition to "work list not empty".

@@ -142,6 +142,7 @@ struct sweeptt_ctx {
   unsigned* d_worklist = nullptr;
   unsigned* d_key = nullptr;   // per-tile activation keys
   unsigned* d_tmax = nullptr;  // per-tile upper bound of the largest travel time (downwind filter)
+  unsigned* d_busy = nullptr;  // per-tile "on a list / being relaxed" flags (single-launch scheduling)
   float min_slowness = 0.f;    // exact minimum of the model (device reduction); < 0: negative/NaN values present
   float bucket = -1.f;         // bucket width in travel-time units (<0: relax every dirty tile each round)
   double mean_slowness = 0;
@@ -279,7 +280,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
-  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
+  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -530,14 +531,14 @@ static int choose_kernel(sweeptt_ctx* c) {
   if (force && atoi(force) >= rxy) { rxy = tiled_variant_for_radius(atoi(force)); stock = 0; }
   CK(tiled_prepare(rxy, stock, c->device, &c->tl));
   {
-    // Share the star's columns out between the compute warps (kernels.cu, c_psplit): every column group
-    // is split between nw "fine parts"; a tile with nlive live units runs P = nw/nlive parts per unit,
-    // part p = fine parts [p*nlive, (p+1)*nlive).  Groups: the k-pattern groups for a stock-star kernel
-    // (one unrolled code block each), else plain chunks of the column list (the generic kernel reads every
-    // column's mask at run time).  Each column goes to the least loaded coarse part (pair of fine parts),
-    // then to the lighter half of it; a group's columns are then ordered by fine part.  Cost model of a
-    // column: its k offsets (packed math) + a constant for the window loads.  Fine parts 0/1 carry the
-    // owner's finishing work, booked as a head start.
+    // Share the star's columns out between the compute warps (kernels.cu, c_psplit).  Column groups: the
+    // k-pattern groups for a stock-star kernel (one unrolled code block each), else plain chunks of the
+    // column list (the generic kernel reads every column's mask at run time).  Every warp walks ALL groups
+    // in the same order and runs a contiguous piece of each, so the pieces of a group are just cut points.
+    // Three tables: a tile with one live unit spreads it over all nw warps (table 0); with two live units
+    // each gets nw/2 warps (tables 1 and 2).  Some warps have other duties and get a head start (cost units,
+    // 1 unit = one k offset of one column): the unit owners finish the tile (min cells, pin, stores), the
+    // feeder warp drives the TMA ring, the finisher warp wakes the neighbours and keeps the books.
     const int nw = c->tl.nw;
     const int ncols = (int)c->dev_columns.size();
     std::vector<int> gbeg;
@@ -550,34 +551,74 @@ static int choose_kernel(sweeptt_ctx* c) {
       c->pat_begin = gbeg;
     }
     const int ngroups = (int)gbeg.size() - 1;
-    std::vector<double> load(nw, 0.0);
-    double head = 12.0;  // measured on config 3 (16 sources): 0 -> 54.4 ms, 5 -> 53.5, 8 -> 50.6, 11 -> 49.9, 14 -> 49.8, 18 -> 50.0
-    if (const char* e = getenv("SWEEPTT_OWNER_BIAS")) head = atof(e);
-    load[0] = head;
-    if (nw > 1) load[1] = head;
-    c->psplit.assign((size_t)MAX_PATTERNS * (MAX_WARPS + 1), 0);
-    std::vector<PullColumn> ordered;
-    ordered.reserve(ncols);
-    for (int g = 0; g < ngroups; ++g) {
-      std::vector<std::vector<PullColumn>> mine(nw);
-      for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) {
-        const double w = (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
-        int best = 0;
-        double bl = 1e300;
-        for (int cp = 0; cp < nw; cp += 2) {
-          const double l = load[cp] + (cp + 1 < nw ? load[cp + 1] : 0.0);
-          if (l < bl) { bl = l; best = cp; }
-        }
-        if (best + 1 < nw && load[best + 1] < load[best]) ++best;
-        mine[best].push_back(c->dev_columns[col]);
-        load[best] += w;
+    // head starts (measured on config 2): round-based kernels 8 / 2 / 14; the single-launch kernel's finisher
+    // also issues two device-wide fences per tile, whose latency is worth ~50 cost units (13.9 -> 12.8 ms)
+    double bias[2][3] = {{8.0, 2.0, 14.0}, {6.0, 2.0, 50.0}};
+    if (const char* e = getenv("SWEEPTT_BIAS"))
+      sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &bias[0][0], &bias[0][1], &bias[0][2], &bias[1][0], &bias[1][1], &bias[1][2]);
+    const int feeder = nw / 2 - 1, finisher = nw - 1;  // warp indices (kernels.cu)
+    c->psplit.assign((size_t)6 * MAX_PATTERNS * (MAX_WARPS + 1), 0);
+    for (int table = 0; table < 6; ++table) {  // 0-2: round-based kernels, 3-5: single-launch kernels
+      const int parts = table % 3 == 0 ? nw : nw / 2;
+      const int warp0 = table % 3 == 2 ? nw / 2 : 0;  // first warp of this table's unit
+      const double b_own = bias[table / 3][0], b_feed = bias[table / 3][1], b_fin = bias[table / 3][2];
+      std::vector<double> load(parts, 0.0);
+      for (int pt = 0; pt < parts; ++pt) {
+        const int w = warp0 + pt;
+        if (pt == 0) load[pt] += b_own;
+        if (w == feeder) load[pt] += b_feed;
+        if (w == finisher) load[pt] += b_fin;
       }
-      for (int f = 0; f <= MAX_WARPS; ++f) {
-        c->psplit[(size_t)g * (MAX_WARPS + 1) + f] = (unsigned short)ordered.size();
-        if (f < nw) ordered.insert(ordered.end(), mine[f].begin(), mine[f].end());
+      for (int g = 0; g < ngroups; ++g) {
+        double gcost = 0;
+        for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) gcost += (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
+        double total = gcost;
+        for (double l : load) total += l;
+        // water-filling level: parts already above it get nothing from this group
+        double level = total / parts;
+        for (int iter = 0; iter < parts; ++iter) {
+          double sum = gcost;
+          int n = 0;
+          for (double l : load) if (l < level) { sum += l; ++n; }
+          const double nl = n ? sum / n : level;
+          if (std::fabs(nl - level) < 1e-9) break;
+          level = nl;
+        }
+        unsigned short* row = &c->psplit[((size_t)table * MAX_PATTERNS + g) * (MAX_WARPS + 1)];
+        // columns per part: its deficit below the level in units of the group's mean column cost, rounded by
+        // largest remainder so that the counts add up (what rounding costs a part here it gets back from
+        // the next groups, because the level is recomputed from the actual loads)
+        const int n = gbeg[g + 1] - gbeg[g];
+        const double wavg = gcost / std::max(1, n);
+        std::vector<int> cntp(parts, 0);
+        std::vector<std::pair<double, int>> frac;
+        int given = 0;
+        for (int pt = 0; pt < parts; ++pt) {
+          const double x = std::max(0.0, level - load[pt]) / wavg;
+          cntp[pt] = (int)std::floor(x);
+          given += cntp[pt];
+          frac.push_back({x - std::floor(x), pt});
+        }
+        std::sort(frac.begin(), frac.end(), [](const std::pair<double, int>& u, const std::pair<double, int>& v) {
+          return u.first > v.first || (u.first == v.first && u.second < v.second);
+        });
+        for (int i = 0; given < n; i = (i + 1) % parts) { cntp[frac[i].second] += 1; ++given; }
+        for (int i = parts - 1; given > n; i = (i + parts - 1) % parts)
+          if (cntp[frac[i].second] > 0) { cntp[frac[i].second] -= 1; --given; }
+        int col = gbeg[g];
+        for (int pt = 0; pt < parts; ++pt) {
+          row[pt] = (unsigned short)col;
+          for (int k = 0; k < cntp[pt]; ++k, ++col)
+            load[pt] += (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
+        }
+        for (int pt = parts; pt <= MAX_WARPS; ++pt) row[pt] = (unsigned short)gbeg[g + 1];
+      }
+      if (getenv("SWEEPTT_DEBUG")) {
+        fprintf(stderr, "sweeptt: column split table %d loads:", table);
+        for (double l : load) fprintf(stderr, " %.1f", l);
+        fprintf(stderr, "\n");
       }
     }
-    c->dev_columns = ordered;
   }
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
@@ -716,14 +757,16 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
   const size_t ntiles = (size_t)g.ntx * g.nty * g.ntz;
   if (ntiles * numstart > 0xfffffff0ull) return fail("too many tiles (%zu x %d sources) for 32-bit work-list entries", ntiles, numstart);
   if (ntiles * numstart > c->tiles_cap) {
-    dev_free(c, c->d_worklist, c->tiles_cap * 8);
+    dev_free(c, c->d_worklist, c->tiles_cap * 16);
     dev_free(c, c->d_key, (c->tiles_cap + 4) * 4);
     dev_free(c, c->d_tmax, (c->tiles_cap + 4) * 4);
-    c->d_worklist = nullptr; c->d_key = nullptr; c->d_tmax = nullptr;
+    dev_free(c, c->d_busy, (c->tiles_cap + 4) * 4);
+    c->d_worklist = nullptr; c->d_key = nullptr; c->d_tmax = nullptr; c->d_busy = nullptr;
     c->tiles_cap = ntiles * numstart;
-    if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 8)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 16)) return 0;
     if (!dev_alloc(c, (void**)&c->d_key, (c->tiles_cap + 4) * 4)) return 0;
     if (!dev_alloc(c, (void**)&c->d_tmax, (c->tiles_cap + 4) * 4)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_busy, (c->tiles_cap + 4) * 4)) return 0;
     invalidate_graph(c);
   }
   if (numstart != c->nsrc) invalidate_graph(c);
@@ -749,6 +792,7 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.worklist = c->d_worklist;
   a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
   a.key = c->d_key;
+  a.busy = c->d_busy;
   {
     // downwind filter (kernels.cu): needs non-negative slowness; dmin = fl(hd_min * fl(vmin + vmin)) bounds
     // every fl(hd * fl(v_n + v_m)) from below because rounding is monotone
@@ -760,6 +804,7 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
     a.dmin = (a.tmax && std::isfinite(hdmin) && hdmin > 0.f) ? hdmin * two_v : 0.f;
   }
   a.bucket = c->bucket;
+  a.bin_scale = c->bucket > 0.f ? 32.0f / c->bucket : 0.f;
   a.tile_pulls = c->d_tile_pulls;
   a.ncols = (int)c->dev_columns.size();
   a.nextra = (int)c->star.extra.size();
@@ -767,6 +812,11 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.max_inner = c->max_inner;
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   a.npat = (int)c->pat_begin.size() - 1;
+  {
+    double look = 4.0;  // in tiles per persistent CTA (measured on config 2: 0 -> 14.1 ms, 1.5 -> 13.8, 2.5 -> 13.4, 4 -> 12.9, 6 -> 12.9)
+    if (const char* e = getenv("SWEEPTT_LOOKAHEAD")) look = atof(e);
+    a.lookahead = (unsigned)std::max(0.0, look * c->tl.grid_persistent);
+  }
   return a;
 }
 
@@ -1056,9 +1106,45 @@ static int run_groups(sweeptt_ctx* c, int want, sweeptt_stats* stats) {
   return 1;
 }
 
+// Single-launch solve (kernels.cu, relax_tiled<..., PERSIST>): reset, one persistent launch, read the state.
+static bool persistent_eligible(sweeptt_ctx* c) {
+  if (c->kernel_used != SWEEPTT_KERNEL_TILED || c->opts.max_rounds > 0) return false;
+  if (const char* e = getenv("SWEEPTT_PERSIST")) { if (atoi(e) == 0) return false; }
+  int loop = c->opts.loop;
+  if (const char* env = getenv("SWEEPTT_LOOP")) {
+    if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
+    if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
+  }
+  if (loop == SWEEPTT_LOOP_BATCHED) return false;
+  const size_t keys = (size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz;
+  return keys <= tiled_persistent_max_keys(c->tl.rxy);
+}
+static int run_persistent(sweeptt_ctx* c, sweeptt_stats* stats) {
+  const RelaxArgs a = make_args(c);
+  CK(cudaEventRecord(c->ev0, c->stream));
+  CK(launch_reset(a, 0, c->stream));
+  CK(launch_persist_begin(a, c->stream));
+  CK(cudaEventRecord(c->ev2, c->stream));
+  CK(launch_relax_persistent(c->tl, c->tm_slow, c->tm_tt, a, c->stream));
+  CK(cudaEventRecord(c->ev1, c->stream));
+  if (!read_state(c)) return 0;
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0, kms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  CK(cudaEventElapsedTime(&kms, c->ev2, c->ev1));
+  const SolveState& h = *c->h_state;
+  fill_stats(c, stats, 0, 6, 1, kms);
+  if (stats) stats->solve_ms = ms;
+  if (h.done != 1u) return fail("single-launch solve stopped without reaching the fixed point (state %u)", h.done);
+  // the round-based view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
+  CK(launch_reset_state_only(a.st, c->opts.max_rounds, c->stream));
+  return 1;
+}
+
 extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
   if (!ready(c)) return 0;
   if (stats) { std::memset(stats, 0, sizeof *stats); }
+  if (persistent_eligible(c)) return run_persistent(c, stats);
   {
     int loop = c->opts.loop;
     if (const char* env = getenv("SWEEPTT_LOOP")) {
