@@ -36,7 +36,8 @@ def test_random_cases(seed, monkeypatch):
     rng = np.random.default_rng(1000 + seed)
     dims, v, off, starts, label = _case(rng)
     knobs = {"SWEEPTT_BUCKET": rng.choice(["-1", "0.5", "2", "8"]), "SWEEPTT_GROUPS": rng.choice(["1", "2", "3"]),
-             "SWEEPTT_SPLIT": rng.choice(["1", "2"]), "SWEEPTT_INNER": rng.choice(["1", "2", "3"])}
+             "SWEEPTT_PERSIST": rng.choice(["0", "1"]), "SWEEPTT_LOOKAHEAD": rng.choice(["0", "0.03", "4"]),
+             "SWEEPTT_INNER": rng.choice(["1", "2", "3"])}
     for k, val in knobs.items():
         monkeypatch.setenv(k, str(val))
     kernel = int(rng.choice([api.KERNEL_AUTO, api.KERNEL_SIMPLE]))

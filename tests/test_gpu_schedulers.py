@@ -1,0 +1,76 @@
+"""GPU (-m gpu): the two schedulers of the tiled kernel -- the single persistent launch that builds its
+work lists on the device (generations, early builds, busy flags) and the CUDA graph of bulk-synchronous
+rounds -- must produce the same bits, for key counts on both sides of the shared-memory snapshot limit
+and for every early-build distance."""
+import numpy as np
+import pytest
+
+import oracle
+import uoparallel_seismic_project_b200 as P
+from uoparallel_seismic_project_b200 import api, workloads as W
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(v, off, starts, monkeypatch, **env):
+    for k in ("SWEEPTT_PERSIST", "SWEEPTT_LOOKAHEAD", "SWEEPTT_PERSIST_MAX_KEYS", "SWEEPTT_BUCKET"):
+        monkeypatch.delenv(k, raising=False)
+    for k, val in env.items():
+        monkeypatch.setenv(k, str(val))
+    with P.SweepContext(kernel=api.KERNEL_TILED) as ctx:
+        ctx.set_model(v); ctx.set_star(off); ctx.set_sources(starts)
+        st = ctx.run()
+        tt = [ctx.get_tt(s) for s in range(len(starts))]
+        viol = [ctx.count_violations(s) for s in range(len(starts))]
+    return tt, st, viol
+
+
+def test_single_launch_is_one_launch_and_equals_the_graph_of_rounds(monkeypatch):
+    v = W.heterogeneous_field((97, 83, 61), seed=5)
+    off = W.star("818")
+    starts = [(48, 41, 60), (0, 0, 0), (96, 82, 30)]
+    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1)
+    b, sb, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0)
+    assert sa.relax_launches == 1 and sb.relax_launches > 1
+    assert va == [0, 0, 0] and vb == [0, 0, 0]
+    for s in range(len(starts)):
+        assert_bit_equal(a[s], b[s], f"source {s}: single launch vs rounds")
+    ref, _, _ = oracle.solve(v[:24, :20, :18].copy(), off, (3, 4, 5))
+    c, _, vc = _solve(v[:24, :20, :18].copy(), off, [(3, 4, 5)], monkeypatch, SWEEPTT_PERSIST=1)
+    assert vc == [0]
+    assert_bit_equal(c[0], ref, "single launch vs oracle")
+
+
+@pytest.mark.parametrize("look", ["0", "0.02", "0.3", "2", "16"])
+def test_every_early_build_distance(look, monkeypatch):
+    v = W.contrast_field((70, 64, 40), seed=9)
+    off = W.star("5")
+    starts = [(10, 60, 39), (69, 0, 0)]
+    base, _, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0)
+    got, st, vg = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1, SWEEPTT_LOOKAHEAD=look)
+    assert st.relax_launches == 1 and vb == [0, 0] and vg == [0, 0]
+    for s in range(2):
+        assert_bit_equal(got[s], base[s], f"lookahead {look}, source {s}")
+
+
+@pytest.mark.parametrize("name,nsrc", [("3", 3), ("818", 9)])
+def test_key_snapshot_in_global_memory_when_the_ring_is_too_small(name, nsrc, monkeypatch):
+    # 241x241x51 = 6727 tiles per source: 3 sources exceed the 3-FS kernel's ring (16 Ki words),
+    # 9 sources the 818-FS kernel's (53 Ki words)
+    v = W.heterogeneous_field((241, 241, 51), seed=7)
+    off = W.star(name)
+    starts = W.starts(111)[:nsrc]
+    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1)
+    b, sb, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0)
+    assert sa.relax_launches == 1 and sb.relax_launches > 1
+    assert va == [0] * nsrc and vb == [0] * nsrc
+    for s in range(nsrc):
+        assert_bit_equal(a[s], b[s], f"{name}-FS source {s}")
+
+
+def test_problems_beyond_the_key_limit_use_the_graph_of_rounds(monkeypatch):
+    v = W.random_field((30, 30, 30), seed=1)
+    _, st, viol = _solve(v, W.star("818"), [(1, 2, 3)], monkeypatch, SWEEPTT_PERSIST_MAX_KEYS=8)
+    assert st.relax_launches > 1 and viol == [0]

@@ -389,8 +389,10 @@ constexpr int TILE_BUILD = -3;    // staged instead of a tile: this CTA popped t
 // Build generation `g_new` from the activation keys (the device-side counterpart of compact_fused, run by
 // ONE CTA while the others keep relaxing): smallest pending key -> bucket threshold -> counting sort of the
 // selected tiles by key into work list (g_new & 1).  Tiles that are still on a list or being relaxed
-// (busy) are left for a later generation, so a tile is never relaxed by two CTAs at once.  `cache` is the
-// CTA's idle TMA ring.  Nothing pending and nothing in flight = fixed point.
+// (busy) are left for a later generation, so a tile is never relaxed by two CTAs at once.  `cache` takes a
+// snapshot of the keys (other CTAs keep lowering them while the three passes run): the CTA's idle TMA ring,
+// or a global scratch array for problems with more keys than that.  Nothing pending and nothing in flight =
+// fixed point.
 template <int NCT>
 __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* cache, bool early) {
   __shared__ unsigned s_min, s_inflight, s_stop;
@@ -603,7 +605,10 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
           const int role = s_role;
           __syncthreads();
           if (role == 2) {
-            build_generation<NCT>(a, s_gen + 1u, reinterpret_cast<unsigned*>(ring), early);
+            // key snapshot: the idle TMA ring when every key fits it, else a global scratch array
+          const size_t nkeys = (size_t)a.nsrc * ntiles;
+          build_generation<NCT>(a, s_gen + 1u,
+                                nkeys <= (size_t)4 * D::BOX_STRIDE ? reinterpret_cast<unsigned*>(ring) : a.keysnap, early);
             fence_proxy_async_all();  // the ring was written through the generic proxy; TMA fills it next
             __syncthreads();
             break;

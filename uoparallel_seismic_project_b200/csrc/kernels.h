@@ -46,6 +46,7 @@ struct RelaxArgs {
   float dmin;                  // lower bound (>= 0) of every edge delay fl(hd*fl(v_n+v_m)) of this model and star
   unsigned* busy;              // nsrc * ntiles: 1 while a tile is on a published list or being relaxed (single-launch
                                // scheduling only: such a tile is never put on a second list)
+  unsigned* keysnap;           // nsrc * ntiles scratch words: key snapshot of the generation builder (large problems)
   float bin_scale;             // 32 / bucket (0 when bucket < 0): key -> sort bin of the generation builder
   float bucket;                // only tiles with key <= (smallest key) + bucket run in a round; <0 = all
   const unsigned long long* tile_pulls;  // per tile position: in-bounds pulls of one visit
@@ -61,8 +62,7 @@ cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow
                                const CUtensorMap& tm_tt, const RelaxArgs& a, cudaStream_t stream);
 // Single-launch solve: ONE persistent launch relaxes to the fixed point; the CTAs build the next work
 // list ("generation") themselves as soon as the current one is handed out, so there is no round barrier,
-// no per-round launch and no tail.  Needs every key of the problem to fit the kernel's shared memory
-// (tiled_persistent_max_keys) and launch_reset + launch_persist_begin on the same stream before it.
+// no per-round launch and no tail.  Needs launch_reset + launch_persist_begin on the same stream before it.
 cudaError_t launch_relax_persistent(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
                                     const RelaxArgs& a, cudaStream_t stream);
 cudaError_t launch_persist_begin(const RelaxArgs& a, cudaStream_t stream);

@@ -143,6 +143,7 @@ struct sweeptt_ctx {
   unsigned* d_key = nullptr;   // per-tile activation keys
   unsigned* d_tmax = nullptr;  // per-tile upper bound of the largest travel time (downwind filter)
   unsigned* d_busy = nullptr;  // per-tile "on a list / being relaxed" flags (single-launch scheduling)
+  unsigned* d_keysnap = nullptr;  // key snapshot of the device-side list builder
   float min_slowness = 0.f;    // exact minimum of the model (device reduction); < 0: negative/NaN values present
   float bucket = -1.f;         // bucket width in travel-time units (<0: relax every dirty tile each round)
   double mean_slowness = 0;
@@ -280,7 +281,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
-  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
+  cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_keysnap); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -761,12 +762,14 @@ extern "C" int sweeptt_set_sources(sweeptt_ctx* c, const struct START* starts, i
     dev_free(c, c->d_key, (c->tiles_cap + 4) * 4);
     dev_free(c, c->d_tmax, (c->tiles_cap + 4) * 4);
     dev_free(c, c->d_busy, (c->tiles_cap + 4) * 4);
-    c->d_worklist = nullptr; c->d_key = nullptr; c->d_tmax = nullptr; c->d_busy = nullptr;
+    dev_free(c, c->d_keysnap, (c->tiles_cap + 4) * 4);
+    c->d_worklist = nullptr; c->d_key = nullptr; c->d_tmax = nullptr; c->d_busy = nullptr; c->d_keysnap = nullptr;
     c->tiles_cap = ntiles * numstart;
     if (!dev_alloc(c, (void**)&c->d_worklist, c->tiles_cap * 16)) return 0;
     if (!dev_alloc(c, (void**)&c->d_key, (c->tiles_cap + 4) * 4)) return 0;
     if (!dev_alloc(c, (void**)&c->d_tmax, (c->tiles_cap + 4) * 4)) return 0;
     if (!dev_alloc(c, (void**)&c->d_busy, (c->tiles_cap + 4) * 4)) return 0;
+    if (!dev_alloc(c, (void**)&c->d_keysnap, (c->tiles_cap + 4) * 4)) return 0;
     invalidate_graph(c);
   }
   if (numstart != c->nsrc) invalidate_graph(c);
@@ -793,6 +796,7 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.cap = (unsigned)((size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz);
   a.key = c->d_key;
   a.busy = c->d_busy;
+  a.keysnap = c->d_keysnap;
   {
     // downwind filter (kernels.cu): needs non-negative slowness; dmin = fl(hd_min * fl(vmin + vmin)) bounds
     // every fl(hd * fl(v_n + v_m)) from below because rounding is monotone
@@ -1116,8 +1120,12 @@ static bool persistent_eligible(sweeptt_ctx* c) {
     if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
   }
   if (loop == SWEEPTT_LOOP_BATCHED) return false;
+  // one CTA builds every list: beyond a few million keys the graph of bulk-synchronous rounds (whose
+  // compaction runs on the whole device, and whose launches are long enough to make tails irrelevant) takes over
+  size_t max_keys = 4u << 20;
+  if (const char* e = getenv("SWEEPTT_PERSIST_MAX_KEYS")) max_keys = (size_t)atoll(e);
   const size_t keys = (size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz;
-  return keys <= tiled_persistent_max_keys(c->tl.rxy);
+  return keys <= max_keys;
 }
 static int run_persistent(sweeptt_ctx* c, sweeptt_stats* stats) {
   const RelaxArgs a = make_args(c);
