@@ -58,11 +58,11 @@ def test_every_early_build_distance(look, monkeypatch):
 @pytest.mark.parametrize("name,nsrc", [("3", 3), ("818", 9)])
 def test_key_snapshot_in_global_memory_when_the_ring_is_too_small(name, nsrc, monkeypatch):
     # 241x241x51 = 6727 tiles per source: 3 sources exceed the 3-FS kernel's ring (16 Ki words),
-    # 9 sources the 818-FS kernel's (53 Ki words)
+    # 9 sources the 818-FS kernel's (53 Ki words); by default such problems run as a graph of rounds
     v = W.heterogeneous_field((241, 241, 51), seed=7)
     off = W.star(name)
     starts = W.starts(111)[:nsrc]
-    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1)
+    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1, SWEEPTT_PERSIST_MAX_KEYS=4000000)
     b, sb, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0)
     assert sa.relax_launches == 1 and sb.relax_launches > 1
     assert va == [0] * nsrc and vb == [0] * nsrc

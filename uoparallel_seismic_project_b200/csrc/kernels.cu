@@ -700,7 +700,10 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (g == h1) {
               // the entry `lookahead` before the list's end is the trigger: whoever pops it builds the next
               // generation right after that tile, so that the new list is out when this one runs dry
-              if (a.lookahead != 0u && pop_c > 2u * a.lookahead && pop_i + a.lookahead == pop_c) build_next = true;
+              // (short lists: not before the fraction trig_q8/256 of the list is handed out)
+              if (a.lookahead != 0u && pop_c >= 64u &&
+                  pop_i == max(pop_c > a.lookahead ? pop_c - a.lookahead : 0u, (pop_c * a.trig_q8) >> 8))
+                build_next = true;
               if (pop_i >= pop_c && ld_volatile_u32(&S->gen) != pop_g) {
                 // this generation is handed out and the next one is already published: take the next tile
                 // from it right here (the CTA then never leaves its pipeline); else the CTA goes to the switch

@@ -54,6 +54,7 @@ struct RelaxArgs {
   int max_inner;               // in-tile relaxation passes per visit (>= 1)
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
   unsigned lookahead;          // single launch: the list entry this far before the end triggers the next build
+  unsigned trig_q8;            // ... but not before this fraction (in 1/256) of the list is handed out
   int npat;                    // pattern groups (generic kernel; the stock kernels know theirs at compile time)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };

@@ -817,9 +817,12 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   a.npat = (int)c->pat_begin.size() - 1;
   {
-    double look = 4.0;  // in tiles per persistent CTA (measured on config 2: 0 -> 14.1 ms, 1.5 -> 13.8, 2.5 -> 13.4, 4 -> 12.9, 6 -> 12.9)
+    double look = 8.0;  // in tiles per persistent CTA (measured on config 2: 0 -> 14.1 ms, 1.5 -> 13.8, 2.5 -> 13.4, 4 -> 12.9, 8 -> 12.9)
     if (const char* e = getenv("SWEEPTT_LOOKAHEAD")) look = atof(e);
     a.lookahead = (unsigned)std::max(0.0, look * c->tl.grid_persistent);
+    double frac = 0.4;  // (0.9 -> 14.8 ms, 0.6 -> 13.1, 0.4 -> 12.9, 0.1 -> 13.2)
+    if (const char* e = getenv("SWEEPTT_TRIGGER_FRAC")) frac = atof(e);
+    a.trig_q8 = (unsigned)std::min(255.0, std::max(0.0, frac * 256.0));
   }
   return a;
 }
@@ -1120,9 +1123,11 @@ static bool persistent_eligible(sweeptt_ctx* c) {
     if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
   }
   if (loop == SWEEPTT_LOOP_BATCHED) return false;
-  // one CTA builds every list: beyond a few million keys the graph of bulk-synchronous rounds (whose
-  // compaction runs on the whole device, and whose launches are long enough to make tails irrelevant) takes over
-  size_t max_keys = 4u << 20;
+  // One CTA builds every list.  While all keys fit its idle TMA ring (53 Ki keys for 818-FS: 8 sources on a
+  // 241x241x51 box) a build takes a few microseconds and hides behind the early-build lookahead; with a
+  // snapshot in global memory it does not (measured: 16 sources 65 ms against 50 ms for the graph of rounds,
+  // whose compaction runs on the whole device and whose launches are long enough to make tails irrelevant).
+  size_t max_keys = tiled_persistent_max_keys(c->tl.rxy);
   if (const char* e = getenv("SWEEPTT_PERSIST_MAX_KEYS")) max_keys = (size_t)atoll(e);
   const size_t keys = (size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz;
   return keys <= max_keys;
