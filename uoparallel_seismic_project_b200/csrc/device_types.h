@@ -94,6 +94,6 @@ struct StarDev {   // star as the simple kernel / verifier read it (global memor
 constexpr int MAX_COLUMNS = 320;
 constexpr int MAX_PATTERNS = 31;
 constexpr int MAX_COL_HD = 4096;
-constexpr int MAX_EXTRA = 512;
+constexpr int MAX_EXTRA = 256;
 
 }  // namespace sweeptt

@@ -43,19 +43,20 @@ namespace sweeptt {
 __constant__ ColumnDev c_cols[MAX_COLUMNS];
 __constant__ float c_col_hd[MAX_COL_HD];
 __constant__ ExtraDev c_extra[MAX_EXTRA];
-// c_psplit[(t * MAX_PATTERNS + g) * (MAX_WARPS + 1) + p]: first column of part p within column group g; part p
-// runs the columns [c_psplit[..][p], c_psplit[..][p + 1]) of EVERY group, so all warps walk the pattern code
-// blocks in the same order (instruction-cache locality) and the host can balance the parts' total cost.
-// Table t = 0: one live unit shared by all nw warps; t = 1, 2: units 0 and 1 of a tile with two live units;
-// t = 3..5: the same for the single-launch kernels (their finisher warp needs a longer head start).
-__constant__ unsigned short c_psplit[6 * MAX_PATTERNS * (MAX_WARPS + 1)];
+// c_pdesc[(t * MAX_PATTERNS + g) * MAX_WARPS + p]: the piece of column group g that part p runs, one 64-bit
+// constant load per group: x = first column | (end column << 16), y = index of the first column's first
+// half-distance.  Every part walks ALL groups in the same order (instruction-cache locality) and the host
+// balances the parts' total cost.  Table t = 0: one live unit shared by all nw warps; t = 1, 2: units 0 and 1
+// of a tile with two live units; t = 3..5: the same for the single-launch kernels (their finisher warp needs a
+// longer head start).
+__constant__ uint2 c_pdesc[6 * MAX_PATTERNS * MAX_WARPS];
 
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, const unsigned short* psplit, int npsplit,
+                                  const ExtraDev* extra, int nextra, const uint2* pdesc, int npdesc,
                                   cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
-  if (npsplit > 0)
-    e = cudaMemcpyToSymbolAsync(c_psplit, psplit, sizeof(unsigned short) * npsplit, 0, cudaMemcpyHostToDevice, stream);
+  if (npdesc > 0)
+    e = cudaMemcpyToSymbolAsync(c_pdesc, pdesc, sizeof(uint2) * npdesc, 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
   if (ncols > 0)
     e = cudaMemcpyToSymbolAsync(c_cols, cols, sizeof(ColumnDev) * ncols, 0, cudaMemcpyHostToDevice, stream);
@@ -308,28 +309,29 @@ __device__ __forceinline__ void relax_offsets_runtime(uint32_t kmask, const floa
   }
 }
 
-// The columns of pattern group G share the compile-time k-pattern KMASK (branch-free unrolled block);
-// this warp runs ITS sub-range [lo,hi) of them (c_psplit).  A group's half-distances are contiguous in
-// column order, so their addresses are pure arithmetic.  Window loads are single-buffered: with 16
-// warps per SM the other warps hide the shared-memory latency.
+// The columns of a pattern group share the compile-time k-pattern KMASK (branch-free unrolled block);
+// this warp runs ITS piece [lo,hi) of them (descriptor `d`, see c_pdesc).  A group's half-distances are
+// contiguous in column order, so their addresses are pure arithmetic.  Window loads are single-buffered:
+// with 16 warps per SM the other warps hide the shared-memory latency.
 template <uint32_t KMASK>
 __device__ __forceinline__ void run_pattern_range(const float* __restrict__ sv, const float* __restrict__ st, int b0,
-                                                  int pb, int lo, int hi_, const float (&vn)[KZ],
+                                                  const uint2 d, const float (&vn)[KZ],
                                                   const u64 (&vnE)[KZ / 2], const u64 (&vnO)[KZ / 2 - 1], u64 nz2,
                                                   float (&acc)[KZ]) {
   constexpr uint32_t GM = granules_of(KMASK);
   constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
+  const int lo = (int)(d.x & 0xffffu), hi_ = (int)(d.x >> 16);
   if (lo >= hi_) return;
-  const int hi0 = c_cols[pb].hd_begin;
+  int hi = (int)d.y;
   float W[WIN], T[WIN];
-  for (int c = lo; c < hi_; ++c) {
+  for (int c = lo; c < hi_; ++c, hi += NK) {
     const int soff = c_cols[c].soff;
     load_window<GM>(sv + b0 + soff, st + b0 + soff, W, T);
-    relax_column<KMASK>(W, T, hi0 + (c - pb) * NK, vn, vnE, vnO, nz2, acc);
+    relax_column<KMASK>(W, T, hi, vn, vnE, vnO, nz2, acc);
   }
 }
 
-// `f0`: index of this warp's first cut point of group 0 in c_psplit; `after(g)` runs after pattern group g-1 (the ring feeder's hooks)
+// `f0`: index of this warp's descriptor of group 0 in c_pdesc; `after(g)` runs after pattern group g-1 (the ring feeder's hooks)
 template <typename HOOK, uint32_t... M>
 __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
                                               const float* __restrict__ st, int b0, const RelaxArgs& a, int f0,
@@ -346,7 +348,8 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
 #pragma unroll
     for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
     for (int g = 0; g < a.npat; ++g) {
-      const int lo = c_psplit[g * (MAX_WARPS + 1) + f0], hi_ = c_psplit[g * (MAX_WARPS + 1) + f0 + 1];
+      const uint2 d = c_pdesc[g * MAX_WARPS + f0];
+      const int lo = (int)(d.x & 0xffffu), hi_ = (int)(d.x >> 16);
       for (int c = lo; c < hi_; ++c) {
         const ColumnDev col = c_cols[c];
         const float* pv = sv + b0 + col.soff;
@@ -367,8 +370,7 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
     }
   } else {
     int g = 0;
-    ((run_pattern_range<M>(sv, st, b0, a.pat_begin[g], c_psplit[g * (MAX_WARPS + 1) + f0],
-                           c_psplit[g * (MAX_WARPS + 1) + f0 + 1], vn, vnE, vnO, nz2, acc),
+    ((run_pattern_range<M>(sv, st, b0, c_pdesc[g * MAX_WARPS + f0], vn, vnE, vnO, nz2, acc),
       ++g, after(g, (int)sizeof...(M))),
      ...);
   }
@@ -654,7 +656,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int nlive = (UNITS == 2 && x0 + 4 < a.g.nx) ? 2 : 1;
     const int P = NW / nlive;
     const int unit = wq / P, part = wq - unit * P;
-    const int f0 = (((PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * (MAX_WARPS + 1) + part;  // c_psplit index, group 0
+    const int f0 = (((PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
     const bool owner = part == 0;
     const int x = (unit << 2) | (lane >> 3);
     // smem float index of this thread's window start for the (0,0) column

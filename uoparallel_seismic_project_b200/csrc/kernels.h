@@ -27,7 +27,7 @@ int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed)
 
 // Upload the column tables into __constant__ memory (stream ordered).
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, const unsigned short* psplit, int npsplit,
+                                  const ExtraDev* extra, int nextra, const uint2* pdesc, int npdesc,
                                   cudaStream_t stream);
 
 struct RelaxArgs {

@@ -669,7 +669,17 @@ static int upload_constants(sweeptt_ctx* c) {
   mix(cols.data(), cols.size() * sizeof(ColumnDev));
   mix(hd_packed.data(), hd_packed.size() * sizeof(float));
   mix(ex.data(), ex.size() * sizeof(ExtraDev));
-  mix(c->psplit.data(), c->psplit.size() * sizeof(unsigned short));
+  // per (table, group, part): the part's piece of the group + where its half-distances start (kernels.cu c_pdesc)
+  std::vector<uint2> pdesc((size_t)6 * MAX_PATTERNS * MAX_WARPS, make_uint2(0u, 0u));
+  for (int table = 0; table < 6; ++table)
+    for (int g = 0; g + 1 < (int)c->pat_begin.size() && g < MAX_PATTERNS; ++g)
+      for (int pt = 0; pt < MAX_WARPS; ++pt) {
+        const unsigned short* row = &c->psplit[((size_t)table * MAX_PATTERNS + g) * (MAX_WARPS + 1)];
+        const unsigned lo = row[pt], hi = row[pt + 1];
+        pdesc[((size_t)table * MAX_PATTERNS + g) * MAX_WARPS + pt] =
+            make_uint2(lo | (hi << 16), lo < hi ? (unsigned)cols[lo].hd_begin : 0u);
+      }
+  mix(pdesc.data(), pdesc.size() * sizeof(uint2));
   auto sg = g_const_sig.find(c->device);
   if (sg != g_const_sig.end() && sg->second == sig && it != g_const_owner.end()) {
     g_const_owner[c->device] = c;
@@ -680,7 +690,7 @@ static int upload_constants(sweeptt_ctx* c) {
   // a different context may still be running with the old tables on another stream
   if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
   CK(upload_star_constants(cols.data(), (int)cols.size(), hd_packed.data(), (int)hd_packed.size(), ex.data(),
-                           (int)ex.size(), c->psplit.data(), (int)c->psplit.size(), c->stream));
+                           (int)ex.size(), pdesc.data(), (int)pdesc.size(), c->stream));
   CK(cudaStreamSynchronize(c->stream));  // host vectors die here
   g_const_owner[c->device] = c;
   c->consts_rxy = c->tl.rxy;
