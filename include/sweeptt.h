@@ -52,7 +52,9 @@ enum {
 enum {
   SWEEPTT_LOOP_AUTO = 0,
   SWEEPTT_LOOP_BATCHED = 1, /* K rounds enqueued per host poll of the device flag          */
-  SWEEPTT_LOOP_GRAPH = 2    /* CUDA graph with a device-evaluated WHILE node (no host poll) */
+  SWEEPTT_LOOP_GRAPH = 2    /* device-resident loop (no host poll): ONE persistent launch that builds
+                               its own work lists while the activation keys fit its shared memory,
+                               else a CUDA graph with a device-evaluated WHILE node              */
 };
 
 typedef struct sweeptt_opts {

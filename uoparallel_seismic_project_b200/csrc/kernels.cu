@@ -9,21 +9,26 @@
 // because fl(a+c) is monotone in a and travel times only ever decrease.
 //
 // Kernels
-//   relax_tiled<RXY>  persistent CTAs steal dirty tiles from a device work list; TMA
-//                     (cp.async.bulk.tensor) stages the tile's slowness and travel-time boxes
-//                     plus the star-radius halo into shared memory behind an mbarrier; each
-//                     thread owns KZ=8 consecutive z nodes and, per (i,j) column of the star,
-//                     pulls a 24-float register window of both arrays with LDS.128 and runs
-//                     the column's k offsets out of registers; changed tiles mark their 27
-//                     neighbours dirty; results leave as 128-bit stores.
-//   compact_dirty     turns the dirty flags into the next round's work list, advances the
-//                     device-resident round counter and feeds the CUDA-graph WHILE condition.
+//   relax_tiled<RXY, STAR, NW, PERSIST>
+//                     persistent CTAs take tiles (8x8x8 nodes = two 4x8x8 units) from a device work list;
+//                     a 2-stage TMA ring (cp.async.bulk.tensor + mbarriers) streams each tile's slowness and
+//                     travel-time boxes plus the star-radius halo through shared memory; the star's (i,j)
+//                     columns of a unit are shared out between the CTA's warps, each thread owns KZ=8
+//                     consecutive z nodes and pulls a 24-float register window of both arrays per column
+//                     (LDS.128), running the column's k offsets out of registers with packed fp32x2 math;
+//                     the parts meet in per-node min cells in shared memory; changed tiles wake their
+//                     neighbours (activation keys, downwind filter); results leave as 128-bit stores.
+//                     PERSIST: the whole solve is ONE launch -- the CTAs build the next work list
+//                     (build_generation) themselves, ahead of time, while the others keep relaxing.
+//   compact_fused / scan_min_key + select_tiles
+//                     round-based scheduling: turn the activation keys into the next round's work list,
+//                     advance the device-resident round counter and feed the CUDA-graph WHILE condition.
 //   relax_simple      one thread per node, global memory, explicit bounds tests: the
 //                     verification path and the fallback for stars wider than the halo.
 //   count_violations  the fixed-point invariant (testconvergence,
 //                     old/wavefront-openmp/wave-multistart.c:300-347) on the device.
-//   fill/pad/unpad/init_sources  the device float-box pool's utilities
-//                     (boxsetall/boxput, include/floatbox.h:176-199).
+//   fill/pad/unpad/init_sources/min_slowness/merge_halo  the device float-box pool's utilities
+//                     (boxsetall/boxput, include/floatbox.h:176-199) and the slab halo min-merge.
 #include "kernels.h"
 
 #include <cuda_runtime.h>
