@@ -74,3 +74,20 @@ def test_problems_beyond_the_key_limit_use_the_graph_of_rounds(monkeypatch):
     v = W.random_field((30, 30, 30), seed=1)
     _, st, viol = _solve(v, W.star("818"), [(1, 2, 3)], monkeypatch, SWEEPTT_PERSIST_MAX_KEYS=8)
     assert st.relax_launches > 1 and viol == [0]
+
+
+def test_single_launch_schedule_is_nondeterministic_but_the_field_is_not(monkeypatch):
+    """The order in which CTAs pop, build and wake is timing dependent; the converged bits must not be
+    (tools/stress_persistent.py is the long version of this)."""
+    v = W.heterogeneous_field((97, 83, 61), seed=5)
+    off = W.star("818")
+    starts = [(48, 41, 60), (0, 0, 0)]
+    first = None
+    for rep in range(6):
+        tt, st, viol = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1,
+                              SWEEPTT_LOOKAHEAD=["8", "0", "0.05"][rep % 3], SWEEPTT_BUCKET=["2", "0.5"][rep % 2])
+        assert st.relax_launches == 1 and viol == [0, 0]
+        if first is None:
+            first = tt
+        for s in range(2):
+            assert_bit_equal(tt[s], first[s], f"repeat {rep}, source {s}")
