@@ -868,17 +868,6 @@ extern "C" int sweeptt_reset(sweeptt_ctx* c) {
   return 1;
 }
 
-static int enqueue_round(sweeptt_ctx* c, const RelaxArgs& a, unsigned long long cond) {
-  if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
-    CK(launch_relax_tiled(c->tl, c->tm_slow, c->tm_tt, a, c->stream));
-    CK(launch_compact(a, cond, c->stream));
-  } else {
-    CK(launch_relax_simple(a, c->d_star, c->nstar, (unsigned long long)c->pulls_per_round * c->nsrc, c->stream));
-    CK(launch_advance_simple(c->d_state, cond, c->stream));
-  }
-  return 1;
-}
-
 static int read_state(sweeptt_ctx* c) {
   CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
