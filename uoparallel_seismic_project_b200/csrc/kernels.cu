@@ -405,7 +405,7 @@ __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* c
   __shared__ unsigned s_min, s_inflight, s_stop;
   __shared__ unsigned s_bin[GEN_BINS + 1];
   SolveState* S = a.st;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.y * 32 + threadIdx.x;  // (32, NW) blocks
   const unsigned total = (unsigned)((size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz);
   unsigned* wl = a.worklist + (size_t)(g_new & 3u) * a.cap;
   for (unsigned spins = 0;; ++spins) {
@@ -498,7 +498,9 @@ __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* c
 //             (atomicMin on the float bits: travel times are >= 0) and part 0 of the unit (the owner)
 //             finishes: start-point pin, changed test, 128-bit stores, activation of the neighbours.
 template <int RXY, typename STAR, int NW, bool PERSIST>
-__global__ void __launch_bounds__(32 * NW, (RXY == 2) ? 3 : 1)
+// exact block shape (32, NW): threadIdx.y IS the warp index, which lets ptxas treat the per-warp column loops as
+// warp-uniform control flow (no BSSY/BSYNC around them)
+__global__ void __block_size__((32, NW, 1))
 relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__ CUtensorMap tm_tt,
             const __grid_constant__ RelaxArgs a) {
   using D = TileDims<RXY>;
@@ -517,9 +519,9 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   __shared__ unsigned s_tmin;  // float bits of the smallest travel time the tile lowered
   __shared__ unsigned s_tmax;  // float bits of the largest travel time of the tile's in-grid nodes
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int wq = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp index, provably warp-uniform
+  const int lane = threadIdx.x;
+  const int wq = threadIdx.y;  // warp index
+  const int tid = wq * 32 + lane;
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1);
     fence_mbar_init();
@@ -1233,9 +1235,9 @@ static void launch_variant(const TiledLaunch& tl, const CUtensorMap& tm_slow, co
                            const RelaxArgs& a, bool persistent, cudaStream_t stream) {
   constexpr int NW = warps_for<RXY>();
   if (persistent)
-    relax_tiled<RXY, STAR, NW, true><<<tl.grid_persistent, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+    relax_tiled<RXY, STAR, NW, true><<<tl.grid_persistent, dim3(32, NW, 1), tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
   else
-    relax_tiled<RXY, STAR, NW, false><<<tl.grid, 32 * NW, tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
+    relax_tiled<RXY, STAR, NW, false><<<tl.grid, dim3(32, NW, 1), tl.smem_bytes, stream>>>(tm_slow, tm_tt, a);
 }
 __global__ void compact_fused(const RelaxArgs a, unsigned long long cond);
 cudaError_t tiled_prepare(int rxy, int stock_id, int device, TiledLaunch* out) {
