@@ -365,6 +365,7 @@ def run_ours(args):
                            "(FADD, FMUL, FADD, FMNMX; no FMA allowed by the bit-exactness contract)",
             "hbm": {"achieved": tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9
                     if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9 / hbm_peak) if k_ms else None,
                     "note": "12 B per node per tile visit; the path is ~50x away from the HBM roof (SURVEY.md 8d)"},
             "traffic": _ncu_traffic(),
         },
