@@ -1284,14 +1284,16 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
   CK(cudaEventRecord(c->ev2, c->stream));
   if (!sweeptt_set_model(c, slowness, nx, ny, nz)) return 0;
   CK(cudaEventRecord(c->ev3, c->stream));
+  CK(cudaEventSynchronize(c->ev3));
+  float h2d_ms = 0;  // read now: the run below reuses these events
+  CK(cudaEventElapsedTime(&h2d_ms, c->ev2, c->ev3));
   const bool same_star = c->have_star && (int)c->fs.size() == starsize &&
                          std::memcmp(c->fs.data(), fs, sizeof(FS) * starsize) == 0;
   if (!same_star && !sweeptt_set_star(c, fs, starsize)) return 0;
   if (!sweeptt_set_sources(c, starts, numstart)) return 0;
   if (!sweeptt_run(c, st)) return 0;
   float ms = 0;
-  CK(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
-  st->h2d_ms = ms;
+  st->h2d_ms = h2d_ms;
   st->h2d_bytes = (long long)nx * ny * nz * 4;
   CK(cudaEventRecord(c->ev2, c->stream));
   // device -> host: un-pad into the dense staging box, then one contiguous copy per source
