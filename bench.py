@@ -188,9 +188,9 @@ def _ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     try:
         t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
+        return t["dram_bytes_per_launch"], t["source"]
     except Exception:
-        return None
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -367,7 +367,10 @@ def run_ours(args):
                     if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9 / hbm_peak) if k_ms else None,
                     "note": "12 B per node per tile visit; the path is ~50x away from the HBM roof (SURVEY.md 8d)"},
-            "traffic": _ncu_traffic(),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch (= per solve) of the config-2 capture
+            "traffic": _ncu_traffic()[0] if args.workload == "config2" else None,
+            "traffic_source": _ncu_traffic()[1] if args.workload == "config2" else None,
+            "algorithmic_bytes_per_launch": tile_bytes * (tiles / args.steps),
         },
     }
     if not args.no_cpu_baseline and world == 1 and args.workload == "config2":
