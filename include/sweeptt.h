@@ -117,6 +117,14 @@ void sweeptt_star_fill_distances(struct FS *fs, int starsize, float delta);
 int sweeptt_build_pull_star(const struct FS *fs, int starsize, int star_used, int32_t *ijk_out,
                             float *half_d_out, int32_t *guard_out, int capacity);
 
+/* Test hook (no device needed): how the tiled kernel shares the star's (i,j) columns out between `nw` warps.
+ * Columns are grouped by k pattern; kmasks_out[c] is column c's pattern in group order; cuts holds six tables
+ * of cut points, cuts[(t * ngroups + g) * (nw + 1) + p] = first column of part p's contiguous piece of group
+ * g (entry nw = end of the group).  Returns the number of columns, or -1 if a capacity is too small. */
+int sweeptt_debug_column_split(const struct FS *fs, int starsize, int nw, int *ngroups_out,
+                               unsigned short *cuts, int cuts_capacity, unsigned *kmasks_out,
+                               int kmasks_capacity);
+
 /* ---- one-shot solve: host buffers in, host buffers out -------------------- */
 
 /* Replaces `void cudaRun(int numstart, int starsize)` (cuda/cudasweep-tt-multistart.cu:80,227)

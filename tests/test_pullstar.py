@@ -1,6 +1,7 @@
 """CPU: the host-side edge-set analysis (product code, csrc/pullstar.cpp through the C ABI).
 A numpy float32 Jacobi over the pull star it returns must reach the reference's field."""
 import numpy as np
+import pytest
 
 import oracle
 import uoparallel_seismic_project_b200 as P
@@ -78,3 +79,35 @@ def test_star_used_override_and_zero_offset():
     assert not any((o == 0).all() for o in ijk)
     ijk_all, _, guard_all = P.build_pull_star(W.star("3"), star_used=98)
     assert guard_all.sum() == 0 and len(ijk_all) == 98
+
+
+@pytest.mark.parametrize("name,nw", [("818", 16), ("5", 16), ("3", 4), ("3", 16)])
+def test_column_split_covers_every_column_once_and_balances_the_warps(name, nw):
+    """The tiled kernel shares a star's columns out between its warps with cut points computed on the host
+    (csrc/pullstar.cpp split_columns): every table must partition every pattern group, and the warps' total
+    costs (popcount + 1.5 per column, plus the head starts of the owner / feeder / finisher warps) must be level."""
+    import uoparallel_seismic_project_b200 as P
+    from uoparallel_seismic_project_b200 import api, workloads as W
+    kmasks, cuts = api.column_split(W.star(name), nw)
+    cost = np.array([bin(int(m)).count("1") + 1.5 for m in kmasks])
+    gbeg = [0] + [i for i in range(1, len(kmasks)) if kmasks[i] != kmasks[i - 1]] + [len(kmasks)]
+    assert cuts.shape == (6, len(gbeg) - 1, nw + 1)
+    bias = [(8.0, 2.0, 14.0), (6.0, 2.0, 50.0)]
+    for t in range(6):
+        parts = nw if t % 3 == 0 else nw // 2
+        warp0 = nw // 2 if t % 3 == 2 else 0
+        load = np.zeros(parts)
+        for pt in range(parts):
+            w = warp0 + pt
+            load[pt] += bias[t // 3][0] * (pt == 0) + bias[t // 3][1] * (w == nw // 2 - 1) + bias[t // 3][2] * (w == nw - 1)
+        for g in range(len(gbeg) - 1):
+            row = cuts[t, g].astype(int)
+            assert row[0] == gbeg[g] and row[parts] == gbeg[g + 1], (t, g)
+            assert all(row[p] <= row[p + 1] for p in range(nw)), (t, g)
+            assert all(row[p] == gbeg[g + 1] for p in range(parts, nw + 1)), (t, g)
+            for pt in range(parts):
+                load[pt] += cost[row[pt]:row[pt + 1]].sum()
+        # level: no warp more than one heavy column (16.5 cost units) above the mean -- where there is enough
+        # work to level at all (a small star forced into the 16-warp kernel has less cost than head starts)
+        if cost.sum() / parts > 60:
+            assert load.max() - load.mean() <= 16.5 + 1e-9, (name, nw, t, load)

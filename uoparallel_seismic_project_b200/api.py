@@ -85,7 +85,7 @@ def lib_path() -> pathlib.Path:
 
 _EXPORTS = [
     "sweeptt_device_count", "sweeptt_device_info", "sweeptt_last_error", "sweeptt_version",
-    "sweeptt_star_fill_distances", "sweeptt_build_pull_star", "sweeptt_solve", "sweeptt_release_cache",
+    "sweeptt_star_fill_distances", "sweeptt_build_pull_star", "sweeptt_debug_column_split", "sweeptt_solve", "sweeptt_release_cache",
     "sweeptt_create", "sweeptt_destroy", "sweeptt_set_stream", "sweeptt_set_model", "sweeptt_set_star",
     "sweeptt_set_sources", "sweeptt_run", "sweeptt_step", "sweeptt_reset", "sweeptt_get_tt", "sweeptt_put_tt",
     "sweeptt_count_violations", "sweeptt_relaxations_per_round", "sweeptt_pool_bytes", "sweeptt_solve_slabs",
@@ -204,6 +204,24 @@ def build_pull_star(star, star_used: int = 0, delta: float = 10.0):
     if n < 0:
         raise SweepError("sweeptt_build_pull_star failed")
     return ijk[:n].copy(), hd[:n].copy(), gd[:n].copy()
+
+
+def column_split(star, nw: int, delta: float = 10.0):
+    """Test hook: (kmasks uint32[C], cuts uint16[6, G, nw+1]) -- how the tiled kernel shares the star's columns
+    out between `nw` warps (six tables, see include/sweeptt.h)."""
+    fs = _as_star(star, delta)
+    lib = load_library()
+    lib.sweeptt_debug_column_split.argtypes = [C.POINTER(FS), C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_int]
+    lib.sweeptt_debug_column_split.restype = C.c_int
+    cuts = np.zeros(6 * 64 * (nw + 1), np.uint16)
+    kmasks = np.zeros(4096, np.uint32)
+    ng = C.c_int(0)
+    n = lib.sweeptt_debug_column_split(fs, len(fs), nw, C.byref(ng), cuts.ctypes.data, cuts.size, kmasks.ctypes.data,
+                                       kmasks.size)
+    if n < 0:
+        raise SweepError("sweeptt_debug_column_split failed")
+    return kmasks[:n].copy(), cuts[: 6 * ng.value * (nw + 1)].reshape(6, ng.value, nw + 1).copy()
 
 
 def solve(slowness, star, starts, *, delta: float = 10.0, out=None, device: int | None = None,

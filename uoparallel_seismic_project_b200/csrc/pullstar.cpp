@@ -96,4 +96,98 @@ long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1
   return total;
 }
 
+void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
+                   int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
+                   std::vector<double>* loads_out) {
+  const int ngroups = (int)gbeg.size() - 1;
+  const int feeder = nw / 2 - 1, finisher = nw - 1;  // warp indices (kernels.cu)
+  auto cost = [&](int col) { return (double)__builtin_popcount(kmasks[col]) + 1.5; };
+  psplit->assign((size_t)6 * max_groups * (max_warps + 1), 0);
+  if (loads_out) loads_out->assign((size_t)6 * max_warps, 0.0);
+  for (int table = 0; table < 6; ++table) {  // 0-2: round-based kernels, 3-5: single-launch kernels
+    const int parts = table % 3 == 0 ? nw : nw / 2;
+    const int warp0 = table % 3 == 2 ? nw / 2 : 0;  // first warp of this table's unit
+    const double b_own = bias[table / 3][0], b_feed = bias[table / 3][1], b_fin = bias[table / 3][2];
+    std::vector<double> load(parts, 0.0);
+    for (int pt = 0; pt < parts; ++pt) {
+      const int w = warp0 + pt;
+      if (pt == 0) load[pt] += b_own;
+      if (w == feeder) load[pt] += b_feed;
+      if (w == finisher) load[pt] += b_fin;
+    }
+    for (int g = 0; g < ngroups && g < max_groups; ++g) {
+      double gcost = 0;
+      for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) gcost += cost(col);
+      double total = gcost;
+      for (double l : load) total += l;
+      // water-filling level: parts already above it get nothing from this group
+      double level = total / parts;
+      for (int iter = 0; iter < parts; ++iter) {
+        double sum = gcost;
+        int n = 0;
+        for (double l : load) if (l < level) { sum += l; ++n; }
+        const double nl = n ? sum / n : level;
+        if (std::fabs(nl - level) < 1e-9) break;
+        level = nl;
+      }
+      unsigned short* row = &(*psplit)[((size_t)table * max_groups + g) * (max_warps + 1)];
+      // columns per part: its deficit below the level in units of the group's mean column cost, rounded by
+      // largest remainder so that the counts add up (what rounding costs a part here it gets back from
+      // the next groups, because the level is recomputed from the actual loads)
+      const int n = gbeg[g + 1] - gbeg[g];
+      const double wavg = gcost / std::max(1, n);
+      std::vector<int> cntp(parts, 0);
+      std::vector<std::pair<double, int>> frac;
+      int given = 0;
+      for (int pt = 0; pt < parts; ++pt) {
+        const double x = std::max(0.0, level - load[pt]) / wavg;
+        cntp[pt] = (int)std::floor(x);
+        given += cntp[pt];
+        frac.push_back({x - std::floor(x), pt});
+      }
+      std::sort(frac.begin(), frac.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+      });
+      for (int i = 0; given < n; i = (i + 1) % parts) { cntp[frac[i].second] += 1; ++given; }
+      for (int i = parts - 1; given > n; i = (i + parts - 1) % parts)
+        if (cntp[frac[i].second] > 0) { cntp[frac[i].second] -= 1; --given; }
+      int col = gbeg[g];
+      for (int pt = 0; pt < parts; ++pt) {
+        row[pt] = (unsigned short)col;
+        for (int k = 0; k < cntp[pt]; ++k, ++col) load[pt] += cost(col);
+      }
+      for (int pt = parts; pt <= max_warps; ++pt) row[pt] = (unsigned short)gbeg[g + 1];
+    }
+    if (loads_out)
+      for (int pt = 0; pt < parts; ++pt) (*loads_out)[(size_t)table * max_warps + pt] = load[pt];
+  }
+}
+
 }  // namespace sweeptt
+
+// Test hook (tests/test_pullstar.py): the column split of a star for `nw` warps, one pattern group per distinct
+// k mask, default head starts.  Writes 6 * ngroups * (nw + 1) cut points, returns the number of columns or -1.
+extern "C" int sweeptt_debug_column_split(const struct FS* fs, int starsize, int nw, int* ngroups_out,
+                                          unsigned short* cuts, int cuts_capacity, unsigned* kmasks_out,
+                                          int kmasks_capacity) {
+  using namespace sweeptt;
+  PullStar ps = build_pull_star(fs, starsize, 0);
+  std::stable_sort(ps.columns.begin(), ps.columns.end(),
+                   [](const PullColumn& a, const PullColumn& b) { return a.kmask < b.kmask; });
+  std::vector<uint32_t> kmasks;
+  std::vector<int> gbeg;
+  for (size_t i = 0; i < ps.columns.size(); ++i) {
+    if (i == 0 || ps.columns[i].kmask != ps.columns[i - 1].kmask) gbeg.push_back((int)i);
+    kmasks.push_back(ps.columns[i].kmask);
+  }
+  gbeg.push_back((int)ps.columns.size());
+  const int ngroups = (int)gbeg.size() - 1;
+  const double bias[2][3] = {{8.0, 2.0, 14.0}, {6.0, 2.0, 50.0}};
+  std::vector<unsigned short> psplit;
+  split_columns(kmasks, gbeg, nw, ngroups, nw, bias, &psplit, nullptr);
+  if ((int)psplit.size() > cuts_capacity || (int)kmasks.size() > kmasks_capacity) return -1;
+  std::copy(psplit.begin(), psplit.end(), cuts);
+  std::copy(kmasks.begin(), kmasks.end(), kmasks_out);
+  if (ngroups_out) *ngroups_out = ngroups;
+  return (int)kmasks.size();
+}

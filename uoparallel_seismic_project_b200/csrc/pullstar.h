@@ -48,4 +48,15 @@ PullStar build_pull_star(const FS* fs, int starsize, int star_used);
 long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1, int y0, int y1,
                       int z0, int z1);
 
+// Share the star's columns out between the tiled kernel's warps.  `kmasks[c]` = k pattern of column c (its cost
+// is popcount + 1.5), `gbeg` = first column of every column group (+ end).  Six tables of cut points
+// (psplit[(table * max_groups + g) * (max_warps + 1) + part] = first column of the part's contiguous piece of
+// group g): table % 3 == 0 spreads a group over all nw warps (tile with one live unit), 1 and 2 over the warps of
+// unit 0 (warps [0, nw/2)) and unit 1 (warps [nw/2, nw)); tables 0-2 use bias[0], tables 3-5 bias[1] =
+// {owner, feeder, finisher} head starts in cost units (owner = part 0 of a table, feeder = warp nw/2-1,
+// finisher = warp nw-1).  loads (optional): resulting cost per (table, part), bias included.
+void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
+                   int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
+                   std::vector<double>* loads);
+
 }  // namespace sweeptt

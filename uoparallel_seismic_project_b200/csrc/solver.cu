@@ -551,75 +551,22 @@ static int choose_kernel(sweeptt_ctx* c) {
       gbeg.push_back(ncols);
       c->pat_begin = gbeg;
     }
-    const int ngroups = (int)gbeg.size() - 1;
     // head starts (measured on config 2): round-based kernels 8 / 2 / 14; the single-launch kernel's finisher
     // also issues two device-wide fences per tile, whose latency is worth ~50 cost units (13.9 -> 12.8 ms)
     double bias[2][3] = {{8.0, 2.0, 14.0}, {6.0, 2.0, 50.0}};
     if (const char* e = getenv("SWEEPTT_BIAS"))
       sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &bias[0][0], &bias[0][1], &bias[0][2], &bias[1][0], &bias[1][1], &bias[1][2]);
-    const int feeder = nw / 2 - 1, finisher = nw - 1;  // warp indices (kernels.cu)
-    c->psplit.assign((size_t)6 * MAX_PATTERNS * (MAX_WARPS + 1), 0);
-    for (int table = 0; table < 6; ++table) {  // 0-2: round-based kernels, 3-5: single-launch kernels
-      const int parts = table % 3 == 0 ? nw : nw / 2;
-      const int warp0 = table % 3 == 2 ? nw / 2 : 0;  // first warp of this table's unit
-      const double b_own = bias[table / 3][0], b_feed = bias[table / 3][1], b_fin = bias[table / 3][2];
-      std::vector<double> load(parts, 0.0);
-      for (int pt = 0; pt < parts; ++pt) {
-        const int w = warp0 + pt;
-        if (pt == 0) load[pt] += b_own;
-        if (w == feeder) load[pt] += b_feed;
-        if (w == finisher) load[pt] += b_fin;
-      }
-      for (int g = 0; g < ngroups; ++g) {
-        double gcost = 0;
-        for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) gcost += (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
-        double total = gcost;
-        for (double l : load) total += l;
-        // water-filling level: parts already above it get nothing from this group
-        double level = total / parts;
-        for (int iter = 0; iter < parts; ++iter) {
-          double sum = gcost;
-          int n = 0;
-          for (double l : load) if (l < level) { sum += l; ++n; }
-          const double nl = n ? sum / n : level;
-          if (std::fabs(nl - level) < 1e-9) break;
-          level = nl;
-        }
-        unsigned short* row = &c->psplit[((size_t)table * MAX_PATTERNS + g) * (MAX_WARPS + 1)];
-        // columns per part: its deficit below the level in units of the group's mean column cost, rounded by
-        // largest remainder so that the counts add up (what rounding costs a part here it gets back from
-        // the next groups, because the level is recomputed from the actual loads)
-        const int n = gbeg[g + 1] - gbeg[g];
-        const double wavg = gcost / std::max(1, n);
-        std::vector<int> cntp(parts, 0);
-        std::vector<std::pair<double, int>> frac;
-        int given = 0;
-        for (int pt = 0; pt < parts; ++pt) {
-          const double x = std::max(0.0, level - load[pt]) / wavg;
-          cntp[pt] = (int)std::floor(x);
-          given += cntp[pt];
-          frac.push_back({x - std::floor(x), pt});
-        }
-        std::sort(frac.begin(), frac.end(), [](const std::pair<double, int>& u, const std::pair<double, int>& v) {
-          return u.first > v.first || (u.first == v.first && u.second < v.second);
-        });
-        for (int i = 0; given < n; i = (i + 1) % parts) { cntp[frac[i].second] += 1; ++given; }
-        for (int i = parts - 1; given > n; i = (i + parts - 1) % parts)
-          if (cntp[frac[i].second] > 0) { cntp[frac[i].second] -= 1; --given; }
-        int col = gbeg[g];
-        for (int pt = 0; pt < parts; ++pt) {
-          row[pt] = (unsigned short)col;
-          for (int k = 0; k < cntp[pt]; ++k, ++col)
-            load[pt] += (double)__builtin_popcount(c->dev_columns[col].kmask) + 1.5;
-        }
-        for (int pt = parts; pt <= MAX_WARPS; ++pt) row[pt] = (unsigned short)gbeg[g + 1];
-      }
-      if (getenv("SWEEPTT_DEBUG")) {
+    std::vector<uint32_t> kmasks(c->dev_columns.size());
+    for (size_t i = 0; i < kmasks.size(); ++i) kmasks[i] = c->dev_columns[i].kmask;
+    std::vector<double> loads;
+    split_columns(kmasks, gbeg, nw, MAX_PATTERNS, MAX_WARPS, bias, &c->psplit, &loads);
+    if (getenv("SWEEPTT_DEBUG"))
+      for (int table = 0; table < 6; ++table) {
+        const int parts = table % 3 == 0 ? nw : nw / 2;
         fprintf(stderr, "sweeptt: column split table %d loads:", table);
-        for (double l : load) fprintf(stderr, " %.1f", l);
+        for (int pt = 0; pt < parts; ++pt) fprintf(stderr, " %.1f", loads[(size_t)table * MAX_WARPS + pt]);
         fprintf(stderr, "\n");
       }
-    }
   }
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
