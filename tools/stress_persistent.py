@@ -17,6 +17,7 @@ for dims, star, starts in cases:
     v = W.heterogeneous_field(dims, 7)
     ref = None
     for r in range(reps):
+        os.environ["SWEEPTT_PERSIST"] = "1"  # (the 3-FS kernel defaults to the graph of rounds)
         os.environ["SWEEPTT_LOOKAHEAD"] = ["8", "0", "0.05", "2", "30"][r % 5]
         os.environ["SWEEPTT_BUCKET"] = ["2", "0.5", "5", "-1"][r % 4]
         os.environ["SWEEPTT_TRIGGER_FRAC"] = ["0.4", "0", "0.9"][r % 3]

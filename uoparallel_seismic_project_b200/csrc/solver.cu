@@ -797,8 +797,8 @@ static int ready(sweeptt_ctx* c) {
     float hdmax = 0.f;
     for (const auto& p : c->star.all) hdmax = std::max(hdmax, p.hd);
     {
-      // in-tile passes per visit: pays when the star radius is small next to the 8x8x32 tile
-      // (measured: 3-FS 5.7 -> 3.7 ms with 4 passes, 5-FS 11.1 -> 10.7 ms with 2, 818-FS no gain)
+      // in-tile passes per visit: pays when the star radius is small next to the 8x8x8 tile (measured on the
+      // 241x241x51 box: 3-FS 5.1 -> 2.8 ms with 4 passes, 5-FS 9.3 -> 8.6 ms with 2, 818-FS 12.9 -> 13.6 ms)
       int mi = c->tl.rxy <= 2 ? 4 : c->tl.rxy <= 4 ? 2 : 1;
       if (const char* e = getenv("SWEEPTT_INNER")) mi = std::max(1, atoi(e));
       if (mi != c->max_inner) { c->max_inner = mi; invalidate_graph(c); }
@@ -1062,6 +1062,9 @@ static int run_groups(sweeptt_ctx* c, int want, sweeptt_stats* stats) {
 // Single-launch solve (kernels.cu, relax_tiled<..., PERSIST>): reset, one persistent launch, read the state.
 static bool persistent_eligible(sweeptt_ctx* c) {
   if (c->kernel_used != SWEEPTT_KERNEL_TILED || c->opts.max_rounds > 0) return false;
+  // the 3-FS kernel (three 4-warp CTAs per SM, tiles of a few hundred nanoseconds) spends its time in list
+  // switches: measured 4.6 ms against 2.8 ms for the graph of rounds (config 1) -- unless asked for explicitly
+  if (c->tl.nw < MAX_WARPS && !getenv("SWEEPTT_PERSIST")) return false;
   if (const char* e = getenv("SWEEPTT_PERSIST")) { if (atoi(e) == 0) return false; }
   int loop = c->opts.loop;
   if (const char* env = getenv("SWEEPTT_LOOP")) {
