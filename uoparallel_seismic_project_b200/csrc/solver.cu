@@ -149,6 +149,8 @@ struct sweeptt_ctx {
   double mean_slowness = 0;
   size_t tiles_cap = 0;  // nsrc*ntiles the lists/flags were sized for
   unsigned long long* d_tile_pulls = nullptr;
+  int pulls_sig[7] = {0, 0, 0, 0, 0, 0, -1};  // geometry + star generation d_tile_pulls was built for
+  int star_gen = 0;                           // bumped by every sweeptt_set_star
   unsigned long long* d_viol = nullptr;
   float* d_stage = nullptr;  // dense staging box for pad/unpad
   size_t stage_floats = 0;
@@ -419,6 +421,10 @@ static int build_tile_pulls(sweeptt_ctx* c) {
   // per tile position: in-bounds pulls of one visit.  Memoised on the per-axis clipping
   // class so only O(5^3) distinct products are evaluated.
   const BoxGeom& g = c->g;
+  // (a repeated sweeptt_solve on the same geometry and star keeps its table: the cudaFree/cudaMalloc pair below
+  //  costs more than the upload of a 241x241x51 model)
+  const int sig[7] = {g.nx, g.ny, g.nz, g.perm[0], g.perm[1], g.perm[2], c->star_gen};
+  if (c->d_tile_pulls && std::memcmp(sig, c->pulls_sig, sizeof sig) == 0) return 1;
   auto axis_classes = [&](int nt, int T, int n, int r, std::vector<int>& cls, std::vector<std::pair<int, int>>& rep) {
     cls.resize(nt);
     std::map<std::vector<int>, int> seen;
@@ -459,6 +465,7 @@ static int build_tile_pulls(sweeptt_ctx* c) {
   c->d_tile_pulls = nullptr;
   CK(cudaMalloc(&c->d_tile_pulls, table.size() * 8));
   CK(cudaMemcpy(c->d_tile_pulls, table.data(), table.size() * 8, cudaMemcpyHostToDevice));
+  std::memcpy(c->pulls_sig, sig, sizeof sig);
   return 1;
 }
 
@@ -493,6 +500,7 @@ extern "C" int sweeptt_set_star(sweeptt_ctx* c, const struct FS* fs, int starsiz
   CK(cudaMemcpy(c->d_star, sd.data(), sd.size() * sizeof(StarDev), cudaMemcpyHostToDevice));
   c->nstar = (int)sd.size();
   c->have_star = true;
+  c->star_gen += 1;
   c->consts_rxy = -1;
   invalidate_graph(c);
   if (!choose_kernel(c)) return 0;
