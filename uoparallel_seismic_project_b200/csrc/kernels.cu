@@ -1075,26 +1075,38 @@ __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict
         padded[((long long)(x + AX) * g.py + (y + AY)) * g.pz + (z + AZ)];
   }
 }
-// smallest slowness of the model (bits in out[0]; out[1] != 0 when a value is negative or NaN, which
-// switches the downwind filter off): feeds RelaxArgs::dmin
+// Statistics of the model in one pass over the dense staged box: out[0] = float bits of the smallest slowness,
+// out[1] != 0 when a value is negative or NaN (switches the downwind filter off), then (8-byte aligned) the sum
+// (double) and the count (unsigned long long) of the finite values -- the mean only scales the activation bucket.
 __global__ void min_slowness_kernel(const float* __restrict__ dense, long long n, unsigned* out) {
   unsigned m = 0x7f800000u, bad = 0u;
+  double sum = 0.0;
+  unsigned long long cnt = 0ull;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = dense[i];
     if (v >= 0.f) m = min(m, __float_as_uint(v)); else bad = 1u;
+    if (v == v && fabsf(v) != CUDART_INF_F) { sum += (double)v; ++cnt; }
   }
   m = __reduce_min_sync(0xffffffffu, m);
   bad = __reduce_or_sync(0xffffffffu, bad);
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
   if ((threadIdx.x & 31) == 0) {
     atomicMin(&out[0], m);
     if (bad) atomicOr(&out[1], 1u);
+    atomicAdd(reinterpret_cast<double*>(out + 2), sum);
+    atomicAdd(reinterpret_cast<unsigned long long*>(out + 4), cnt);
   }
 }
-cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out2, cudaStream_t stream) {
-  const unsigned init[2] = {0x7f800000u, 0u};
-  cudaError_t e = cudaMemcpyAsync(out2, init, sizeof init, cudaMemcpyHostToDevice, stream);
+cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out6, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out6, 0, 24, stream);
   if (e != cudaSuccess) return e;
-  min_slowness_kernel<<<1184, 256, 0, stream>>>(dense, n, out2);
+  const unsigned inf_bits = 0x7f800000u;
+  e = cudaMemcpyAsync(out6, &inf_bits, 4, cudaMemcpyHostToDevice, stream);  // (pageable 4-byte source: staged at call time)
+  if (e != cudaSuccess) return e;
+  min_slowness_kernel<<<1184, 256, 0, stream>>>(dense, n, out6);
   return cudaGetLastError();
 }
 

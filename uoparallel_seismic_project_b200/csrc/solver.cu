@@ -257,7 +257,7 @@ extern "C" sweeptt_ctx* sweeptt_create(const sweeptt_opts* opts) {
   ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
        cudaMallocHost(&c->h_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-       cudaMalloc(&c->d_viol, sizeof(unsigned long long)) == cudaSuccess;
+       cudaMalloc(&c->d_viol, 32) == cudaSuccess;
   if (!ok) {
     fail("context setup failed on device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
     sweeptt_destroy(c);
@@ -378,30 +378,26 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   }
   c->g = g;
   const size_t dense = (size_t)nx * ny * nz;
-  {
-    // mean slowness of a strided sample: only used to scale the activation bucket (scheduling,
-    // never the arithmetic)
-    double sum = 0;
-    size_t cnt = 0;
-    const size_t step = std::max<size_t>(1, dense / 65536);
-    for (size_t i = 0; i < dense; i += step) {
-      if (std::isfinite(slowness[i])) { sum += slowness[i]; ++cnt; }
-    }
-    c->mean_slowness = cnt ? sum / (double)cnt : 0.0;
-  }
   if (!ensure_stage(c, dense)) return 0;
   CK(launch_fill(c->d_slow, g.vol, std::numeric_limits<float>::infinity(), c->stream));
   CK(cudaMemcpyAsync(c->d_stage, slowness, dense * 4, cudaMemcpyHostToDevice, c->stream));
   CK(launch_pad_box(c->d_stage, c->d_slow, g, c->stream));
   {
     // exact minimum of the model: lower bound of every edge delay for the downwind filter
-    unsigned r[2] = {0, 1};
+    // ... and the mean of the finite values, which only scales the activation bucket (scheduling, never the
+    // arithmetic); one device pass instead of a host loop over the caller's array
+    unsigned r[6] = {0, 1, 0, 0, 0, 0};
     CK(launch_min_slowness(c->d_stage, (long long)dense, reinterpret_cast<unsigned*>(c->d_viol), c->stream));
     CK(cudaMemcpyAsync(r, c->d_viol, sizeof r, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float vmin;
     std::memcpy(&vmin, &r[0], 4);
     c->min_slowness = (r[1] || !std::isfinite(vmin)) ? -1.f : vmin;
+    double sum;
+    unsigned long long cnt;
+    std::memcpy(&sum, &r[2], 8);
+    std::memcpy(&cnt, &r[4], 8);
+    c->mean_slowness = cnt ? sum / (double)cnt : 0.0;
     invalidate_graph(c);
   }
   c->have_model = true;
