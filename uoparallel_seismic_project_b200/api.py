@@ -255,7 +255,7 @@ def solve(slowness, star, starts, *, delta: float = 10.0, out=None, device: int 
 
 
 def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, delta: float = 10.0,
-                max_rounds: int | None = None, verbose: int | None = None):
+                max_rounds: int | None = None, rounds_per_poll: int | None = None, verbose: int | None = None):
     """ONE source on ONE grid decomposed into `num_slabs` 1-D slabs over the visible GPUs (slabs share
     devices round-robin when there are more slabs than GPUs), halo planes min-merged over NVLink
     peer access after every local convergence.  Replaces the MPI ghost-cell programs
@@ -266,7 +266,8 @@ def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, de
     fs = _as_star(star, delta)
     st = START(int(start[0]), int(start[1]), int(start[2]))
     out = np.empty(v.shape, np.float32)
-    o = _opts(num_devices=num_slabs, slab_axis=slab_axis, max_rounds=max_rounds, verbose=verbose)
+    o = _opts(num_devices=num_slabs, slab_axis=slab_axis, max_rounds=max_rounds, rounds_per_poll=rounds_per_poll,
+              verbose=verbose)
     s = _Stats()
     _check(lib.sweeptt_solve_slabs(v.ctypes.data, nx, ny, nz, fs, len(fs), st, out.ctypes.data, C.byref(o), C.byref(s)),
            "sweeptt_solve_slabs")
