@@ -1099,7 +1099,7 @@ static int run_persistent(sweeptt_ctx* c, sweeptt_stats* stats) {
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   CK(cudaEventElapsedTime(&kms, c->ev2, c->ev1));
   const SolveState& h = *c->h_state;
-  fill_stats(c, stats, 0, 6, 1, kms);
+  fill_stats(c, stats, 0, a.tmax ? 7 : 6, 1, kms);  // reset (state, tt, keys, tmax, sources) + list 0 + the solve itself
   if (stats) stats->solve_ms = ms;
   if (h.done != 1u) return fail("single-launch solve stopped without reaching the fixed point (state %u)", h.done);
   // the round-based view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
