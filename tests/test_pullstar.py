@@ -92,7 +92,7 @@ def test_column_split_covers_every_column_once_and_balances_the_warps(name, nw):
     cost = np.array([bin(int(m)).count("1") + 1.5 for m in kmasks])
     gbeg = [0] + [i for i in range(1, len(kmasks)) if kmasks[i] != kmasks[i - 1]] + [len(kmasks)]
     assert cuts.shape == (6, len(gbeg) - 1, nw + 1)
-    bias = [(8.0, 2.0, 14.0), (6.0, 2.0, 50.0)]
+    bias = [(8.0, 2.0, 14.0), (10.0, 2.0, 60.0)]  # csrc/pullstar.h kDefaultBias
     for t in range(6):
         parts = nw if t % 3 == 0 else nw // 2
         warp0 = nw // 2 if t % 3 == 2 else 0

@@ -182,9 +182,8 @@ extern "C" int sweeptt_debug_column_split(const struct FS* fs, int starsize, int
   }
   gbeg.push_back((int)ps.columns.size());
   const int ngroups = (int)gbeg.size() - 1;
-  const double bias[2][3] = {{8.0, 2.0, 14.0}, {6.0, 2.0, 50.0}};
   std::vector<unsigned short> psplit;
-  split_columns(kmasks, gbeg, nw, ngroups, nw, bias, &psplit, nullptr);
+  split_columns(kmasks, gbeg, nw, ngroups, nw, kDefaultBias, &psplit, nullptr);
   if ((int)psplit.size() > cuts_capacity || (int)kmasks.size() > kmasks_capacity) return -1;
   std::copy(psplit.begin(), psplit.end(), cuts);
   std::copy(kmasks.begin(), kmasks.end(), kmasks_out);

@@ -55,6 +55,10 @@ long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1
 // unit 0 (warps [0, nw/2)) and unit 1 (warps [nw/2, nw)); tables 0-2 use bias[0], tables 3-5 bias[1] =
 // {owner, feeder, finisher} head starts in cost units (owner = part 0 of a table, feeder = warp nw/2-1,
 // finisher = warp nw-1).  loads (optional): resulting cost per (table, part), bias included.
+// default head starts {owner, feeder, finisher}: [0] round-based kernels, [1] single-launch kernels, whose finisher
+// also issues two device-wide fences per tile (measured on config 2: 6/2/50 -> 12.9 ms, 10/2/60 -> 12.7 ms)
+constexpr double kDefaultBias[2][3] = {{8.0, 2.0, 14.0}, {10.0, 2.0, 60.0}};
+
 void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
                    int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
                    std::vector<double>* loads);

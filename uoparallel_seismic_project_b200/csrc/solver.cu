@@ -555,9 +555,9 @@ static int choose_kernel(sweeptt_ctx* c) {
       gbeg.push_back(ncols);
       c->pat_begin = gbeg;
     }
-    // head starts (measured on config 2): round-based kernels 8 / 2 / 14; the single-launch kernel's finisher
-    // also issues two device-wide fences per tile, whose latency is worth ~50 cost units (13.9 -> 12.8 ms)
-    double bias[2][3] = {{8.0, 2.0, 14.0}, {6.0, 2.0, 50.0}};
+    // head starts: defaults in pullstar.h
+    double bias[2][3];
+    std::memcpy(bias, kDefaultBias, sizeof bias);
     if (const char* e = getenv("SWEEPTT_BIAS"))
       sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &bias[0][0], &bias[0][1], &bias[0][2], &bias[1][0], &bias[1][1], &bias[1][2]);
     std::vector<uint32_t> kmasks(c->dev_columns.size());
