@@ -435,6 +435,7 @@ __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* c
     const unsigned thr = all ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
     const float scale = a.bin_scale;  // GEN_BINS / bucket, divided on the host (a division here would put FFMAs into
                                       // this kernel's SASS, which tests/test_sass.py keeps free of them)
+#pragma unroll 8  // (the snapshot may live in global memory: keep several loads in flight)
     for (unsigned i = tid; i < total; i += NCT) {
       const unsigned k = cache[i];
       if (k != 0x7f800000u && k <= thr) {
@@ -448,6 +449,7 @@ __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* c
     __syncthreads();
     const unsigned cnt = s_bin[GEN_BINS];
     __syncthreads();
+#pragma unroll 8
     for (unsigned i = tid; i < total; i += NCT) {
       const unsigned k = cache[i];
       if (k != 0x7f800000u && k <= thr) {
