@@ -98,10 +98,10 @@ long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1
 
 void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
                    int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
-                   std::vector<double>* loads_out) {
+                   std::vector<double>* loads_out, double column_overhead) {
   const int ngroups = (int)gbeg.size() - 1;
   const int feeder = nw / 2 - 1, finisher = nw - 1;  // warp indices (kernels.cu)
-  auto cost = [&](int col) { return (double)__builtin_popcount(kmasks[col]) + 1.5; };
+  auto cost = [&](int col) { return (double)__builtin_popcount(kmasks[col]) + column_overhead; };
   psplit->assign((size_t)6 * max_groups * (max_warps + 1), 0);
   if (loads_out) loads_out->assign((size_t)6 * max_warps, 0.0);
   for (int table = 0; table < 6; ++table) {  // 0-2: round-based kernels, 3-5: single-launch kernels

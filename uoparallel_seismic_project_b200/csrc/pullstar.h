@@ -61,6 +61,6 @@ constexpr double kDefaultBias[2][3] = {{8.0, 2.0, 14.0}, {10.0, 2.0, 60.0}};
 
 void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
                    int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
-                   std::vector<double>* loads);
+                   std::vector<double>* loads, double column_overhead = 1.5);
 
 }  // namespace sweeptt

@@ -563,7 +563,9 @@ static int choose_kernel(sweeptt_ctx* c) {
     std::vector<uint32_t> kmasks(c->dev_columns.size());
     for (size_t i = 0; i < kmasks.size(); ++i) kmasks[i] = c->dev_columns[i].kmask;
     std::vector<double> loads;
-    split_columns(kmasks, gbeg, nw, MAX_PATTERNS, MAX_WARPS, bias, &c->psplit, &loads);
+    double col_overhead = 1.5;  // window loads + set-up of a column, in units of one k offset
+    if (const char* e = getenv("SWEEPTT_COLCOST")) col_overhead = atof(e);
+    split_columns(kmasks, gbeg, nw, MAX_PATTERNS, MAX_WARPS, bias, &c->psplit, &loads, col_overhead);
     if (getenv("SWEEPTT_DEBUG"))
       for (int table = 0; table < 6; ++table) {
         const int parts = table % 3 == 0 ? nw : nw / 2;
