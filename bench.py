@@ -49,12 +49,29 @@ def parse():
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region: NVML polled every 2 ms from a thread
+    (the timed region of config 2 is ~0.3 s, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.thread = None
+        self.rows = []          # (sm MHz, max MHz, watts, reasons bitmask)
+        self._stop = False
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE,
@@ -62,7 +79,39 @@ class ClockSampler:
         except OSError:
             pass
 
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(get_reasons(self.h)) if get_reasons else 0
+                self.rows.append((sm, self.mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _stop_nvml(self):
+        self._stop = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        def bit(name, default):
+            return getattr(nv, "nvmlClocksEventReason" + name, getattr(nv, "nvmlClocksThrottleReason" + name, default))
+        bits = {"hw_slowdown": bit("HwSlowdown", 0x8), "hw_thermal_slowdown": bit("HwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": bit("SwThermalSlowdown", 0x20), "sw_power_cap": bit("SwPowerCap", 0x4)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [r[0] for r in self.rows]; pw = [r[2] for r in self.rows]
+        reasons = sorted(n for n, b in bits.items() if any(r[3] & b for r in self.rows))
+        load = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw), "source": "nvml, 2 ms period"}
+
     def stop(self):
+        if self.thread is not None:
+            return self._stop_nvml()
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -88,7 +137,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         load = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw)}
+                "samples": len(sm), "power_w_max": max(pw), "source": "nvidia-smi -lms 50"}
 
 
 # ------------------------------------------------------------------------------------------
