@@ -4,18 +4,21 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): 241x241x51 heterogeneous slowness box (synthetic stand-in,
-seed 7: the reference's velocity files are missing blobs), docs/818-FS.txt,
-docs/start-4-241-241-51.txt.  One *step* = one complete multi-start solve of that batch
-(travel times re-initialised, relaxed to the fixed point).  N>1 is weak scaling: every rank
-solves 4 sources of its own (rank 0: start-4; rank r: the next rows of start-111) on its own
-replica of the box -- no data-path collective.
+Workload (BASELINE.json configs[2] -- the configuration the metric "... 241x241x51 818-FS, 1/2/4/8 B200" is quoted
+on; it fits one GPU): 241x241x51 heterogeneous slowness box (synthetic stand-in, seed 7: the reference's velocity
+files are missing blobs), docs/818-FS.txt, docs/start-111-241-241-51.txt.  One *step* = one complete multi-start
+solve of all 111 sources (travel times re-initialised, relaxed to the fixed point).  N>1 is STRONG scaling: the 111
+sources are dealt round-robin to the ranks (rank r: sources r, r+N, ...; the mpi/backup.c:351-363 scheme), each rank
+solves its share on its own replica of the box -- no data-path collective; the ideal speed-up at 8 GPUs is 111/14.
+`--workload config2` is BASELINE configs[1] (start-4; weak scaling: 4 private sources per GPU); at N=1 it also
+rides along under "extras" together with config 1 (3-FS) and the 5-FS star.
 
 Prints ONE JSON line (rank 0).  metric = GRelax/s: in-bounds (node, offset, source) pull
 evaluations executed per second, summed over GPUs; converged sources/s rides along.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -28,7 +31,12 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 DIMS = (241, 241, 51)
-WORKLOAD = "241x241x51 heterogeneous slowness (synthetic, seed 7), 818-FS, start-4 (4 sources per GPU)"
+WORKLOADS = {
+    "config3": "241x241x51 heterogeneous slowness (synthetic, seed 7), 818-FS, start-111 (111 sources) sharded over the GPUs",
+    "config2": "241x241x51 heterogeneous slowness (synthetic, seed 7), 818-FS, start-4 (4 sources per GPU)",
+    "config4": "1201x1201x251 heterogeneous slowness (synthetic, seed 11), 818-FS, 24 sources (start-24 x5) sharded over the GPUs",
+}
+VISITS_PER_SWEEP_818 = 2_246_171_812   # in-bounds (node, offset) visits of one reference sweep of the 241 box
 
 
 def parse():
@@ -38,10 +46,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
-                    help="config2 (default, the contract's workload): 241 box, 4 sources per GPU, weak scaling; "
-                         "config3: 241 box, start-111 sharded over the GPUs (strong); "
-                         "config4: 1201x1201x251, 24 sources sharded over the GPUs (strong, device-resident only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-1 / config-2 / 5-FS riders at N=1")
+    ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config4"],
+                    help="config3 (default, the contract's workload): 241 box, start-111 sharded over the GPUs (strong); "
+                         "config2: 241 box, 4 sources per GPU (weak); "
+                         "config4: 1201x1201x251, 24 sources sharded over the GPUs (strong, device-resident only). "
+                         "Config 5 (one source, one huge grid over all GPUs) is tools/config5_bench.py.")
     return ap.parse_args()
 
 
@@ -143,9 +153,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own serial code on the host cores
 # ------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _cpu_worker(args):
-    """One process per source (the mpi/backup.c scheme): warm the state with `pre` slices, then
-    time `slices` calls of the reference's sweepXYZ over consecutive slices of the star."""
+    """One process per source (the mpi/backup.c scheme): time consecutive calls of the reference's sweepXYZ over
+    1/8 slices of the star (state carried from call to call)."""
     src, slices, kind = args
     import numpy as np
     import oracle
@@ -180,71 +197,173 @@ def _cpu_worker(args):
     return out
 
 
-def cpu_reference_run(steps, warmup):
-    """Returns (per-step seconds (max over the source processes), visits per step, kind, cores)."""
+def cpu_reference_run(steps, warmup, workload):
+    """All host cores, one source per process (config 3 has 111 sources to hand out, config 2 has 4).
+    Returns (per-step seconds = max over the processes, visits per step, kind, cores)."""
     import multiprocessing as mp
     import oracle
     from uoparallel_seismic_project_b200 import workloads as W
     kind = "reference" if oracle.reference() is not None else "port"
     if kind == "port":
         oracle.restatement()
-    starts = W.starts(4)
-    cores = min(len(starts), os.cpu_count() or 1)
+    starts = W.starts(4) if workload == "config2" else W.starts(111)
+    cores = max(1, min(len(starts), host_cores()))
+    starts = starts[:cores]
     slices = list(range(warmup + steps))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(tuple(int(c) for c in s), slices, kind) for s in starts])
     step_s, step_v = [], []
     for k in range(warmup, warmup + steps):
-        step_s.append(max(r[k][0] for r in res) if cores >= len(starts) else sum(r[k][0] for r in res) / cores)
+        step_s.append(max(r[k][0] for r in res))
         step_v.append(sum(r[k][1] for r in res))
     return step_s, step_v, kind, cores
+
+
+def _ref_sweeps_per_source():
+    """Sweep counts of the reference's own converged runs on this workload (tests/golden, made by tools/make_golden.py)."""
+    n = []
+    for name in ("full_241.json", "full_241_more.json"):
+        try:
+            for g in json.loads((ROOT / "tests" / "golden" / name).read_text()):
+                if g.get("star") == "818" and g.get("kind") == "hetero" and g.get("seed") == 7 and \
+                        tuple(g.get("dims", DIMS)) == DIMS:
+                    n.append(g["ref_sweeps"])
+        except Exception:
+            pass
+    return n
+
+
+def cpu_sample_text(cores, workload):
+    return (f"each step = one call of the reference's sweepXYZ per source over 1/8 of the 818-FS offsets (slices rotate, "
+            f"state carried across steps), {cores} sources in {cores} processes on {cores} host cores (the mpi/backup.c "
+            f"source-sharding scheme; {'start-4' if workload == 'config2' else 'the first rows of start-111'}); "
+            "a CPU visit relaxes both directions of an edge")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    step_s, step_v, kind, cores = cpu_reference_run(args.steps, args.warmup)
+    workload = args.workload if args.workload in ("config2", "config3") else "config3"
+    step_s, step_v, kind, cores = cpu_reference_run(args.steps, args.warmup, workload)
     total_s, total_v = sum(step_s), sum(step_v)
     value = total_v / total_s / 1e9
-    sample = ("each step = one call of sweepXYZ per source over 1/8 of the 818-FS offsets (slices rotate), "
-              "4 sources in 4 processes (the mpi/backup.c source-sharding scheme), state carried across steps")
     line = {
         "impl": "reference", "metric": "GRelax/s", "value": value, "unit": "GRelax/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU reference: (node, offset) visits of serial_new sweepXYZ, "
-                   "each visit relaxes both directions of the edge"},
-        "cpu_baseline": {"value": value, "unit": "GRelax/s", "cores": cores, "kind": kind, "sample": sample},
+        "higher_is_better": True, "scaling": "weak" if workload == "config2" else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[workload],
+                   "note": "CPU reference on ALL host cores whatever --gpus is: (node, offset) visits of serial_new "
+                           "sweepXYZ, each visit relaxes both directions of the edge"},
+        "cpu_baseline": {"value": value, "unit": "GRelax/s", "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(cores, workload)},
         "e2e": {"value": value, "unit": "GRelax/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    try:  # converged sources/s: measured visit rate / (visits per sweep x the reference's recorded sweep counts)
-        gold = json.loads((ROOT / "tests" / "golden" / "full_241.json").read_text())
-        sweeps = [g["ref_sweeps"] for g in gold if g["label"].startswith("config2")]
-        per_sweep = 2_246_171_812
-        line["converged_sources_per_s"] = value * 1e9 / (per_sweep * (sum(sweeps) / len(sweeps)))
-        line["config"]["sources_per_s_note"] = (f"extrapolated: measured visits/s over {sum(sweeps)/len(sweeps):.0f} sweeps per source "
-                                                "(sweep counts recorded from the reference's own converged runs, tests/golden/full_241.json)")
-    except Exception:
-        pass
+    sweeps = _ref_sweeps_per_source()
+    if sweeps:   # converged sources/s: measured visit rate / (visits per sweep x the reference's recorded sweep counts)
+        mean = sum(sweeps) / len(sweeps)
+        line["converged_sources_per_s"] = value * 1e9 / (VISITS_PER_SWEEP_818 * mean)
+        line["config"]["sources_per_s_note"] = (
+            f"extrapolated: measured visits/s over {mean:.1f} sweeps per source (mean of the {len(sweeps)} converged "
+            "reference runs recorded in tests/golden/full_241*.json)")
     print(json.dumps(line), flush=True)
     return 0
 
 
 def _ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture -- only while csrc/kernels.cu is still the file that was profiled (else the number is stale: None)."""
     try:
-        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        t = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
+        sha = hashlib.sha256((ROOT / "uoparallel_seismic_project_b200" / "csrc" / "kernels.cu").read_bytes()).hexdigest()
+        if t.get("kernels_cu_sha256") != sha:
+            return None, f"stale: {t.get('source')} was taken with another kernels.cu"
         return t["dram_bytes_per_launch"], t["source"]
     except Exception:
         return None, None
 
 
+def _golden(label):
+    for name in ("full_241.json", "full_241_more.json"):
+        try:
+            for g in json.loads((ROOT / "tests" / "golden" / name).read_text()):
+                if g["label"] == label:
+                    return g
+        except Exception:
+            pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def timed_resident(P, torch, ctx, stream, flush, steps, warmup, barrier, before_timed=None):
+    """W untimed + K timed device-resident solves (CUDA events on the solve stream, L2 flushed in between)."""
+    for _ in range(warmup):
+        ctx.run()
+    if before_timed:
+        before_timed()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    acc = dict(relaxations=0, launches=0, rounds=0, tiles=0, relax_launches=0)
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        flush.zero_()                      # L2 flush between timed iterations (not timed)
+        ev[k][0].record(stream)
+        st = ctx.run()
+        ev[k][1].record(stream)
+        acc["relaxations"] += st.relaxations; acc["launches"] += st.kernel_launches; acc["rounds"] += st.rounds
+        acc["tiles"] += st.tile_visits; acc["relax_launches"] += st.relax_launches
+    barrier()
+    acc["wall_ms"] = (time.perf_counter() - wall0) * 1e3
+    acc["dev_ms"] = sum(a.elapsed_time(b) for a, b in ev)
+    return acc
+
+
+def kernel_roofline(P, v, star, starts, local, stream, flush, reps, sms, sm_max):
+    """The relax kernel alone: same solve, every launch bracketed with CUDA events on its own stream."""
+    pctx = P.SweepContext(device=local, profile_kernels=1)
+    pctx.set_stream(stream.cuda_stream)
+    pctx.set_model(v); pctx.set_star(star); pctx.set_sources(starts)
+    pctx.run()
+    k_ms = k_launch = k_relax = k_tiles = 0
+    for _ in range(reps):
+        flush.zero_()
+        st = pctx.run()
+        k_ms += st.relax_kernel_ms; k_launch += st.relax_launches; k_relax += st.relaxations; k_tiles += st.tile_visits
+    pctx.close()
+    lane_ops = 4 * k_relax / (k_ms * 1e-3) / 1e12               # Tlane-op/s of the relax kernel alone
+    peak_ops = sms * 128 * sm_max * 1e6 / 1e12
+    return dict(k_ms=k_ms, k_launch=k_launch, k_relax=k_relax, k_tiles=k_tiles, reps=reps, lane_ops=lane_ops,
+                peak_ops=peak_ops)
+
+
+def extras_single_gpu(P, torch, W, local, stream, flush, sms, sm_max):
+    """N=1 riders (short): BASELINE config 2 (start-4, 818-FS), config 1 (constant box, 3-FS, start-1) and the 5-FS
+    star, each device-resident with its own relax-kernel roofline fraction."""
+    out = {}
+    cases = [("config2_818_start4", W.heterogeneous_field(DIMS, 7), "818", W.starts(4)),
+             ("config1_const_3fs_start1", W.constant_field(DIMS), "3", W.starts(1)),
+             ("hetero_5fs_start4", W.heterogeneous_field(DIMS, 7), "5", W.starts(4))]
+    for name, v, starname, starts in cases:
+        star = P.make_star(W.star(starname))
+        ctx = P.SweepContext(device=local)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_model(v); ctx.set_star(star); ctx.set_sources(starts)
+        acc = timed_resident(P, torch, ctx, stream, flush, 5, 3, torch.cuda.synchronize)
+        viol = sum(ctx.count_violations(s) for s in range(len(starts)))
+        ctx.close()
+        r = kernel_roofline(P, v, star, starts, local, stream, flush, 3, sms, sm_max)
+        out[name] = {"ms_per_solve": acc["dev_ms"] / 5, "grelax_per_s": acc["relaxations"] / acc["dev_ms"] / 1e6,
+                     "converged_sources_per_s": len(starts) * 5 / acc["dev_ms"] * 1e3,
+                     "tile_visits_per_solve": acc["tiles"] / 5, "violations": viol,
+                     "roofline_frac": r["lane_ops"] / r["peak_ops"], "relax_launches_per_solve": r["k_launch"] / r["reps"]}
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -269,20 +388,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    global DIMS, WORKLOAD
-    scaling = "weak"
+    dims = DIMS
+    scaling = "strong"
+    src_ids = None
     if args.workload == "config2":
-        v = W.heterogeneous_field(DIMS, 7)
+        v = W.heterogeneous_field(dims, 7)
         starts = dispatch.sources_for_rank(rank, world)
+        scaling = "weak"
     elif args.workload == "config3":
-        v = W.heterogeneous_field(DIMS, 7)
-        starts = W.starts(111)[dispatch.shard_round_robin(111, rank, world)]
-        WORKLOAD, scaling = "241x241x51 heterogeneous slowness (synthetic, seed 7), 818-FS, start-111 sharded over the GPUs", "strong"
+        v = W.heterogeneous_field(dims, 7)
+        src_ids = dispatch.shard_round_robin(111, rank, world)
+        starts = W.starts(111)[src_ids]
     else:
-        DIMS = (1201, 1201, 251)
-        v = W.heterogeneous_field(DIMS, 11)
+        dims = (1201, 1201, 251)
+        v = W.heterogeneous_field(dims, 11)
         starts = (W.starts(24) * 5)[dispatch.shard_round_robin(24, rank, world)]
-        WORKLOAD, scaling = "1201x1201x251 heterogeneous slowness (synthetic, seed 11), 818-FS, 24 sources (start-24 x5) sharded over the GPUs", "strong"
+    workload = WORKLOADS[args.workload]
     star = P.make_star(W.star("818"))
     nsrc = len(starts)
     props = torch.cuda.get_device_properties(local)
@@ -290,76 +411,71 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # ---- device-resident leg: slowness + star + sources already in HBM -------------------------
-    stream = torch.cuda.Stream(device=dev)   # not the legacy default stream: the solver captures a CUDA graph on it
+    stream = torch.cuda.Stream(device=dev)   # not the legacy default stream: the solver captures CUDA graphs on it
     torch.cuda.set_stream(stream)
     ctx = P.SweepContext(device=local)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_model(v); ctx.set_star(star); ctx.set_sources(starts)
-    for _ in range(args.warmup):
-        ctx.run()
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    relax = launches = rounds = tiles = 0
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (not timed)
-        ev[k][0].record(stream)
-        st = ctx.run()
-        ev[k][1].record(stream)
-        relax += st.relaxations; launches += st.kernel_launches; rounds += st.rounds; tiles += st.tile_visits
-    barrier()
-    wall_ms = (time.perf_counter() - wall0) * 1e3
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if sampler else None
-    tot = dispatch.combine(dist, dev, elapsed_ms=dev_ms, relaxations=relax, sources=nsrc * args.steps,
-                           launches=launches)
-    assert all(ctx.count_violations(s) == 0 for s in range(nsrc)), "solve did not reach the fixed point"
+    box = {}
+    acc = timed_resident(P, torch, ctx, stream, flush, args.steps, args.warmup, barrier,
+                         before_timed=lambda: box.setdefault("sampler", ClockSampler(local) if rank == 0 else None))
+    clocks = box["sampler"].stop() if box.get("sampler") else None
+    tot = dispatch.combine(dist, dev, elapsed_ms=acc["dev_ms"], relaxations=acc["relaxations"],
+                           sources=nsrc * args.steps, launches=acc["launches"])
+    pulls_per_grid_round = ctx.relaxations_per_round   # in-bounds pulls of ONE full round of one source (analytic)
+    # ---- parity riders: every rank's fields are fixed points; source 0 against the reference's own hash ----
+    viol = sum(ctx.count_violations(s) for s in range(nsrc))
+    viol_all = dispatch.combine(dist, dev, elapsed_ms=0.0, relaxations=viol, sources=0, launches=0)["relaxations"]
+    parity = {"fixed_point_violations_all_ranks": int(viol_all)}
+    if rank == 0 and args.workload in ("config2", "config3"):
+        tt0 = ctx.get_tt(0)
+        parity["source0_sha256"] = hashlib.sha256(tt0.tobytes()).hexdigest()
+        g = _golden("config3_hetero_818_row0" if args.workload == "config3" else "config2_hetero_818_src0")
+        parity["source0_matches_reference_sha256"] = (g["tt_sha256"] == parity["source0_sha256"]) if g else None
+    assert viol_all == 0, "solve did not reach the fixed point"
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    sm_run = (clocks or {}).get("sm_mhz") or sm_max
 
     # ---- roofline of the dominant kernel (relax_tiled): same steps, every launch event-bracketed --
-    pctx = P.SweepContext(device=local, profile_kernels=1)
-    pctx.set_stream(stream.cuda_stream)
-    pctx.set_model(v); pctx.set_star(star); pctx.set_sources(starts)
-    pctx.run()
-    k_ms = k_launch = k_relax = 0
-    for _ in range(max(1, min(args.steps, 5))):
-        flush.zero_()
-        st = pctx.run()
-        k_ms += st.relax_kernel_ms; k_launch += st.relax_launches; k_relax += st.relaxations
-    pctx.close()
-
+    roof = kernel_roofline(P, v, star, starts, local, stream, flush, max(1, min(args.steps, 5)), sms, sm_max)
     if args.workload == "config4":   # 24 x 1.45 GB of pinned host boxes: the extra workload reports the resident leg only
         ctx.close()
         if rank == 0:
             value = tot["relaxations"] / tot["elapsed_ms"] / 1e6
-            peak = sms * 128 * ((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
             print(json.dumps({"metric": "GRelax/s", "value": value, "unit": "GRelax/s", "n_gpus": world, "steps": args.steps,
                               "warmup": args.warmup, "ms_per_step": tot["elapsed_ms"] / args.steps, "higher_is_better": True,
                               "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                              "config": {"workload": WORKLOAD}, "converged_sources_per_s": tot["sources"] / tot["elapsed_ms"] * 1e3,
-                              "clocks": clocks, "gpu_launches": tot["launches"], "e2e": None,
+                              "config": {"workload": workload}, "converged_sources_per_s": tot["sources"] / tot["elapsed_ms"] * 1e3,
+                              "clocks": clocks, "gpu_launches": tot["launches"], "e2e": None, "parity": parity,
                               "roofline": {"bound": "fp32-issue", "kernel": "relax_tiled<7, fs818>", "unit": "TFLOP/s",
-                                           "achieved": 4 * k_relax / (k_ms * 1e-3) / 1e12, "peak": peak,
-                                           "frac": 4 * k_relax / (k_ms * 1e-3) / 1e12 / peak}}), flush=True)
+                                           "achieved": roof["lane_ops"], "peak": roof["peak_ops"],
+                                           "frac": roof["lane_ops"] / roof["peak_ops"]}}), flush=True)
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
     # ---- end-to-end leg: pinned host buffers through the one-shot C-ABI call ----------------------
     hv = torch.from_numpy(v).pin_memory()
-    hout = torch.empty((nsrc,) + DIMS, dtype=torch.float32).pin_memory()
+    hout = torch.empty((nsrc,) + dims, dtype=torch.float32).pin_memory()
     st_arr = api._make_starts(starts)
     ptrs = (ctypes.c_void_p * nsrc)(*[hout[s].data_ptr() for s in range(nsrc)])
     opts = api._opts(device=local)
     for _ in range(args.warmup):
-        api.solve_raw(hv.data_ptr(), DIMS, star, st_arr, ptrs, opts)
+        api.solve_raw(hv.data_ptr(), dims, star, st_arr, ptrs, opts)
     barrier()
     e2e_relax = 0
+    d2h_tail_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        s2 = api.solve_raw(hv.data_ptr(), DIMS, star, st_arr, ptrs, opts)
+        s2 = api.solve_raw(hv.data_ptr(), dims, star, st_arr, ptrs, opts)
         e2e_relax += s2.relaxations
-        launches_e2e = s2.kernel_launches
+        d2h_tail_ms += s2.d2h_ms
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e = dispatch.combine(dist, dev, elapsed_ms=e2e_ms, relaxations=e2e_relax, sources=nsrc * args.steps, launches=0)
@@ -368,6 +484,14 @@ def run_ours(args):
         assert np.array_equal(got.view(np.uint32), ctx.get_tt(0).view(np.uint32)), "e2e and resident legs disagree"
     ctx.close()
     P.load_library().sweeptt_release_cache()
+    del hout
+
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "config3":
+        try:
+            extras = extras_single_gpu(P, torch, W, local, stream, flush, sms, sm_max)
+        except Exception as e:  # a rider must never sink the headline
+            extras = {"failed": repr(e)}
 
     if rank != 0:
         if dist is not None:
@@ -375,60 +499,60 @@ def run_ours(args):
         return 0
 
     value = tot["relaxations"] / tot["elapsed_ms"] / 1e6          # GRelax/s, whole job
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except OSError:
-        pass
-    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-    sm_run = (clocks or {}).get("sm_mhz") or sm_max
-    lane_ops = 4 * k_relax / (k_ms * 1e-3) / 1e12               # Tlane-op/s of the relax kernel alone
-    peak_ops = sms * 128 * sm_max * 1e6 / 1e12
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tile_bytes = 8 * 8 * 8 * 12                                 # algorithmic bytes per tile visit (8x8x8 nodes x 12 B)
+    launches_per_step = roof["k_launch"] / roof["reps"]
+    alg_bytes_per_launch = tile_bytes * roof["k_tiles"] / max(1, roof["k_launch"])
+    hbm_achieved = tile_bytes * roof["k_tiles"] / (roof["k_ms"] * 1e-3) / 1e9 if roof["k_ms"] else None
+    traffic, traffic_src = _ncu_traffic() if args.workload == "config3" else (None, None)
     line = {
         "metric": "GRelax/s", "value": value, "unit": "GRelax/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot["elapsed_ms"] / args.steps, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sources_per_gpu": nsrc,
-                   "loop": ("single persistent launch per solve (work lists built on the device)" if k_launch <= max(1, min(args.steps, 5))
+        "config": {"workload": workload, "sources_total": tot["sources"] // args.steps, "sources_on_rank0": nsrc,
+                   "loop": (f"{launches_per_step:.0f} single persistent launches per solve (waves of <= 8 sources; work lists "
+                            "built on the device)" if launches_per_step <= 64
                             else "CUDA-graph WHILE of rounds (device-resident)"),
                    "l2": "flushed between timed steps (512 MiB write, untimed)",
                    "relax_definition": "one pull evaluation tt[n] <- min(tt[n], hd*(v_n+v_m)+tt[m]) with n,m in bounds"},
         "converged_sources_per_s": tot["sources"] / tot["elapsed_ms"] * 1e3,
-        "rounds_per_step": rounds / args.steps, "tile_visits_per_step": tiles / args.steps,
-        "wall_ms_timed_region": wall_ms,
+        "rounds_per_step": acc["rounds"] / args.steps, "tile_visits_per_step": acc["tiles"] / args.steps,
+        "pulls_per_source": tot["relaxations"] / max(1, tot["sources"]),
+        "grid_equivalents_per_source": tot["relaxations"] / max(1, tot["sources"]) / pulls_per_grid_round,
+        "wall_ms_timed_region": acc["wall_ms"],
         "clocks": clocks,
         "gpu_launches": tot["launches"],
+        "parity": parity,
         "e2e": {"value": e2e["relaxations"] / e2e["elapsed_ms"] / 1e6, "unit": "GRelax/s",
                 "converged_sources_per_s": e2e["sources"] / e2e["elapsed_ms"] * 1e3,
-                "ms_per_step": e2e["elapsed_ms"] / args.steps, "timing": "host wall clock around sweeptt_solve()",
-                "h2d_bytes_per_step": int(np.prod(DIMS)) * 4, "d2h_bytes_per_step": int(np.prod(DIMS)) * 4 * nsrc},
+                "ms_per_step": e2e["elapsed_ms"] / args.steps,
+                "timing": "host wall clock around sweeptt_solve() (H2D of the model, solve, D2H of every field; the "
+                          "copies of finished waves run behind the solve of the next ones)",
+                "d2h_tail_ms_per_step_rank0": d2h_tail_ms / args.steps,
+                "h2d_bytes_per_step": int(np.prod(dims)) * 4 * world,
+                "d2h_bytes_per_step": int(np.prod(dims)) * 4 * (tot["sources"] // args.steps)},
         "roofline": {
             "bound": "fp32-issue", "kernel": "relax_tiled<7, fs818>",
-            "achieved": lane_ops, "peak": peak_ops, "unit": "TFLOP/s", "frac": lane_ops / peak_ops,
-            "frac_at_run_clock": lane_ops / (sms * 128 * sm_run * 1e6 / 1e12),
-            "grelax_per_s_kernel": k_relax / (k_ms * 1e-3) / 1e9,
-            "avg_launch_ms": k_ms / max(1, k_launch), "launches_measured": k_launch,
+            "achieved": roof["lane_ops"], "peak": roof["peak_ops"], "unit": "TFLOP/s", "frac": roof["lane_ops"] / roof["peak_ops"],
+            "frac_at_run_clock": roof["lane_ops"] / (sms * 128 * sm_run * 1e6 / 1e12),
+            "grelax_per_s_kernel": roof["k_relax"] / (roof["k_ms"] * 1e-3) / 1e9,
+            "avg_launch_ms": roof["k_ms"] / max(1, roof["k_launch"]), "launches_measured": roof["k_launch"],
             "peak_source": f"{sms} SMs x 128 lanes x {sm_max:.0f} MHz (clocks.max.sm), 4 fp32 operations per pull "
                            "(FADD, FMUL, FADD, FMNMX; no FMA allowed by the bit-exactness contract)",
-            "hbm": {"achieved": tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9
-                    if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (tile_bytes * (tiles / args.steps) / (k_ms / max(1, min(args.steps, 5)) * 1e-3) / 1e9 / hbm_peak) if k_ms else None,
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_achieved / hbm_peak if hbm_achieved else None,
                     "note": "12 B per node per tile visit; the path is ~50x away from the HBM roof (SURVEY.md 8d)"},
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch (= per solve) of the config-2 capture
-            "traffic": _ncu_traffic()[0] if args.workload == "config2" else None,
-            "traffic_source": _ncu_traffic()[1] if args.workload == "config2" else None,
-            "algorithmic_bytes_per_launch": tile_bytes * (tiles / args.steps),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_bytes_per_launch,
         },
     }
-    if not args.no_cpu_baseline and world == 1 and args.workload == "config2":
+    if extras is not None:
+        line["extras"] = extras
+    if not args.no_cpu_baseline and world == 1 and args.workload in ("config2", "config3"):
         try:
-            step_s, step_v, kind, cores = cpu_reference_run(2, 1)
-            line["cpu_baseline"] = {
-                "value": sum(step_v) / sum(step_s) / 1e9, "unit": "GRelax/s", "cores": cores, "kind": kind,
-                "sample": "2 timed + 1 warm-up calls of sweepXYZ per source over 1/8 of the 818-FS offsets each, "
-                          "4 sources in 4 processes; a CPU visit relaxes both directions of an edge"}
+            step_s, step_v, kind, cores = cpu_reference_run(2, 1, args.workload)
+            line["cpu_baseline"] = {"value": sum(step_v) / sum(step_s) / 1e9, "unit": "GRelax/s", "cores": cores,
+                                    "kind": kind, "sample": "2 timed + 1 warm-up steps; " + cpu_sample_text(cores, args.workload)}
         except Exception as e:  # the baseline must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "GRelax/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)

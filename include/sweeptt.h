@@ -17,6 +17,11 @@
  *   - there is NO CPU fallback: every compute entry point fails loudly when no
  *     CUDA device / sm_100 kernel image is available.
  *
+ * Threading: a context is used by one host thread at a time.  Different contexts may be driven from different
+ * threads; the forward-star tables live in per-device __constant__ memory, so contexts on ONE device whose stars
+ * differ take turns (each compute call holds a lease on the device's tables for its duration; identical stars
+ * share it).  Concurrent sweeptt_solve() calls for the same device serialise on that device's cached context.
+ *
  * Plain C: no C++ or torch types cross this boundary.
  */
 #ifndef SWEEPTT_H
@@ -189,6 +194,9 @@ int sweeptt_count_violations(sweeptt_ctx *ctx, int source, long long *violations
 long long sweeptt_relaxations_per_round(sweeptt_ctx *ctx);
 /* Bytes of device memory currently held by the context's pool. */
 size_t sweeptt_pool_bytes(sweeptt_ctx *ctx);
+/* Tiles (= activation keys) per source of the current model; the single-launch scheduler takes as many
+ * sources per launch as fit its shared-memory key snapshot, more sources run as consecutive waves. */
+long long sweeptt_tiles_per_source(sweeptt_ctx *ctx);
 
 /* ---- single huge grid: slab decomposition over the devices of one box ----- */
 

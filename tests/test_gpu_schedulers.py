@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _solve(v, off, starts, monkeypatch, **env):
-    for k in ("SWEEPTT_PERSIST", "SWEEPTT_LOOKAHEAD", "SWEEPTT_PERSIST_MAX_KEYS", "SWEEPTT_BUCKET"):
+    for k in ("SWEEPTT_PERSIST", "SWEEPTT_LOOKAHEAD", "SWEEPTT_PERSIST_MAX_KEYS", "SWEEPTT_BUCKET", "SWEEPTT_WAVE"):
         monkeypatch.delenv(k, raising=False)
     for k, val in env.items():
         monkeypatch.setenv(k, str(val))
@@ -62,12 +62,37 @@ def test_key_snapshot_in_global_memory_when_the_ring_is_too_small(name, nsrc, mo
     v = W.heterogeneous_field((241, 241, 51), seed=7)
     off = W.star(name)
     starts = W.starts(111)[:nsrc]
-    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1, SWEEPTT_PERSIST_MAX_KEYS=4000000)
+    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1, SWEEPTT_PERSIST_MAX_KEYS=4000000, SWEEPTT_WAVE=0)
     b, sb, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0)
     assert sa.relax_launches == 1 and sb.relax_launches > 1
     assert va == [0] * nsrc and vb == [0] * nsrc
     for s in range(nsrc):
         assert_bit_equal(a[s], b[s], f"{name}-FS source {s}")
+
+
+def test_more_sources_than_one_launch_holds_run_as_waves_of_single_launches(monkeypatch):
+    """5 sources, room for 2 per launch -> waves of 2 + 2 + 1 persistent launches, each on its own slice of the boxes,
+    keys and work lists; same bits as the graph of rounds over all sources at once and as one-shot sweeptt_solve
+    (whose device->host copies of finished waves run behind the next wave)."""
+    v = W.heterogeneous_field((97, 83, 61), seed=5)
+    off = W.star("818")
+    starts = [(48, 41, 60), (0, 0, 0), (96, 82, 30), (10, 70, 5), (90, 3, 58)]
+    with P.SweepContext(kernel=api.KERNEL_TILED) as probe:
+        probe.set_model(v); probe.set_star(off); probe.set_sources(starts[:1])
+        probe.run()
+        ntiles = probe.tiles_per_source
+    a, sa, va = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=1, SWEEPTT_PERSIST_MAX_KEYS=2 * ntiles + 1)
+    b, sb, vb = _solve(v, off, starts, monkeypatch, SWEEPTT_PERSIST=0, SWEEPTT_WAVE=0)
+    assert sa.relax_launches == 3 and sb.relax_launches > 3
+    assert va == [0] * 5 and vb == [0] * 5
+    for s in range(5):
+        assert_bit_equal(a[s], b[s], f"source {s}: waves vs rounds")
+    monkeypatch.setenv("SWEEPTT_PERSIST_MAX_KEYS", str(2 * ntiles + 1))
+    c, sc = P.solve(v, off, starts, kernel=api.KERNEL_TILED)
+    assert sc.relax_launches == 3 and sc.d2h_bytes == 5 * v.size * 4
+    for s in range(5):
+        assert_bit_equal(c[s], a[s], f"source {s}: sweeptt_solve vs context")
+    P.load_library().sweeptt_release_cache()
 
 
 def test_problems_beyond_the_key_limit_use_the_graph_of_rounds(monkeypatch):

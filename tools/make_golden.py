@@ -4,6 +4,8 @@ serial_new/sweep-tt-multistart.c compiled in the build container).
 
   python tools/make_golden.py small     -> tests/golden/small_cases.npz   (seconds)
   python tools/make_golden.py full      -> tests/golden/full_241.json     (~15-25 min, 5 processes)
+  python tools/make_golden.py more [P]  -> tests/golden/full_241_more.json (round 2: 9 further config-3 sources,
+                                           full-size 5-FS and a scaled config-4-like box; P processes, ~1 h on 6)
 
 The GPU box has no /root/reference; the parity tests there compare against these files.
 Small cases: converged float32 fields for seeded boxes.  Full size (BASELINE configs 1 and 2):
@@ -66,12 +68,13 @@ def small():
 
 
 def _full_one(job):
-    label, kind, seed, star, start = job
-    v = field(kind, (241, 241, 51), seed)
+    label, kind, seed, star, start = job[:5]
+    dims = tuple(job[5]) if len(job) > 5 else (241, 241, 51)
+    v = field(kind, dims, seed)
     t0 = time.time()
     tt, sweeps = oracle.ref_solve(v, W.star(star), start)
     flat = tt.ravel()
-    return dict(label=label, kind=kind, seed=seed, star=star, start=list(map(int, start)), ref_sweeps=sweeps,
+    return dict(label=label, kind=kind, seed=seed, star=star, start=list(map(int, start)), dims=list(dims), ref_sweeps=sweeps,
                 seconds=round(time.time() - t0, 1), v_sha256=hashlib.sha256(v.tobytes()).hexdigest(),
                 tt_sha256=hashlib.sha256(tt.tobytes()).hexdigest(), sample_stride=4999,
                 sample_bits=[int(x) for x in flat[::4999].view(np.uint32)])
@@ -88,5 +91,30 @@ def full():
         print(r["label"], r["ref_sweeps"], r["seconds"], r["tt_sha256"][:16])
 
 
+MORE_C3 = [0, 13, 27, 41, 55, 69, 83, 97, 110]          # rows of docs/start-111-241-241-51.txt
+C4_DIMS = (301, 301, 64)                                 # scaled config-4-like box (seed 11 like config 4)
+C4_STARTS = [(15, 25, 63), (150, 150, 63), (285, 40, 63), (60, 270, 63), (240, 240, 63), (150, 20, 63)]
+
+
+def more():
+    procs = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    jobs = []
+    s111 = W.starts(111)
+    for i in MORE_C3:
+        jobs.append((f"config3_hetero_818_row{i}", "hetero", 7, "818", tuple(int(c) for c in s111[i])))
+    jobs.append(("full_hetero_5fs_start1", "hetero", 7, "5", tuple(int(c) for c in W.starts(1)[0])))
+    jobs.append(("full_const_5fs_start1", "constant", 0, "5", tuple(int(c) for c in W.starts(1)[0])))
+    for s, st in enumerate(C4_STARTS):
+        jobs.append((f"config4like_hetero_818_src{s}", "hetero", 11, "818", st, C4_DIMS))
+    out = GOLD / "full_241_more.json"
+    res = []
+    with mp.Pool(procs) as pool:
+        for r in pool.imap_unordered(_full_one, jobs):
+            res.append(r)
+            res.sort(key=lambda x: x["label"])
+            out.write_text(json.dumps(res, indent=1))     # partial results survive an interrupted run
+            print(r["label"], r["ref_sweeps"], r["seconds"], r["tt_sha256"][:16], flush=True)
+
+
 if __name__ == "__main__":
-    {"small": small, "full": full}[sys.argv[1]]()
+    {"small": small, "full": full, "more": more}[sys.argv[1]]()

@@ -88,7 +88,7 @@ _EXPORTS = [
     "sweeptt_star_fill_distances", "sweeptt_build_pull_star", "sweeptt_debug_column_split", "sweeptt_solve", "sweeptt_release_cache",
     "sweeptt_create", "sweeptt_destroy", "sweeptt_set_stream", "sweeptt_set_model", "sweeptt_set_star",
     "sweeptt_set_sources", "sweeptt_run", "sweeptt_step", "sweeptt_reset", "sweeptt_get_tt", "sweeptt_put_tt",
-    "sweeptt_count_violations", "sweeptt_relaxations_per_round", "sweeptt_pool_bytes", "sweeptt_solve_slabs",
+    "sweeptt_count_violations", "sweeptt_relaxations_per_round", "sweeptt_pool_bytes", "sweeptt_tiles_per_source", "sweeptt_solve_slabs",
     "sweeptt_solve_slabs_vbox", "sweeptt_vbox_dims",
     "sweeptt_vbox_load", "sweeptt_vbox_store", "sweeptt_vbox_load_subset", "sweeptt_text_load",
     "sweeptt_star_load", "sweeptt_starts_load", "sweeptt_write_output_tt", "sweeptt_free",
@@ -133,6 +133,8 @@ def load_library() -> C.CDLL:
     lib.sweeptt_relaxations_per_round.restype = C.c_longlong
     lib.sweeptt_pool_bytes.argtypes = [C.c_void_p]
     lib.sweeptt_pool_bytes.restype = C.c_size_t
+    lib.sweeptt_tiles_per_source.argtypes = [C.c_void_p]
+    lib.sweeptt_tiles_per_source.restype = C.c_longlong
     lib.sweeptt_solve_slabs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FS), C.c_int, START,
                                         C.c_void_p, C.POINTER(_Opts), C.POINTER(_Stats)]
     lib.sweeptt_solve_slabs_vbox.argtypes = [C.c_char_p, C.POINTER(FS), C.c_int, START, C.c_void_p, C.POINTER(_Opts),
@@ -375,6 +377,10 @@ class SweepContext:
     @property
     def relaxations_per_round(self) -> int:
         return self._lib.sweeptt_relaxations_per_round(self._h)
+
+    @property
+    def tiles_per_source(self) -> int:
+        return self._lib.sweeptt_tiles_per_source(self._h)
 
     @property
     def pool_bytes(self) -> int:

@@ -66,8 +66,11 @@ struct SolveState {
   unsigned builder;          // generation some CTA has claimed to build (== gen + 1 while a build is running)
   unsigned done;             // 1 = fixed point reached, 2 = watchdog gave up (error)
   unsigned inflight;         // tiles published on a list and not yet finished
-  unsigned gcount[4];        // entries of generation g's list, at [g & 3]
-  unsigned gcursor[4];       // pop cursor of generation g, at [g & 3]
+  // generation g's list lives in slot g & 3: entry count in the HIGH word, pop cursor in the LOW word.  One
+  // 64-bit word so that a pop (atomicAdd of 1) reads cursor and count of the SAME generation and the builder
+  // recycles a slot with ONE store: a straggler still popping generation g-4 either sees the old, exhausted
+  // pair or takes a valid entry of the new list -- never an entry that is handed out a second time.
+  unsigned long long gslot[4];
 };
 
 struct ColumnDev {

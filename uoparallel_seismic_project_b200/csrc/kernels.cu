@@ -463,9 +463,8 @@ __device__ void build_generation(const RelaxArgs& a, unsigned g_new, unsigned* c
     __syncthreads();
     if (tid == 0) {
       if (cnt != 0) {
-        S->gcount[g_new & 3u] = cnt;
-        S->gcursor[g_new & 3u] = 0u;
-        atomicAdd(&S->inflight, cnt);
+        atomicAdd(&S->inflight, cnt);  // (before the slot: a popped tile can never finish before it is counted)
+        atomicExch(&S->gslot[g_new & 3u], (unsigned long long)cnt << 32);  // count | cursor 0, one store
         S->round += 1;
         __threadfence();
         st_volatile_u32(&S->gen, g_new);
@@ -568,8 +567,9 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       for (;;) {
         if (ld_volatile_u32(&S->done)) return TILE_NONE;
         const unsigned g = s_gen;
-        const unsigned i = atomicAdd(&S->gcursor[g & 3u], 1u);
-        if (i < ld_volatile_u32(&S->gcount[g & 3u])) return (int)__ldcg(&a.worklist[(size_t)(g & 3u) * a.cap + i]);
+        const unsigned long long w = atomicAdd(&S->gslot[g & 3u], 1ull);  // cursor and count of ONE generation
+        const unsigned i = (unsigned)w;
+        if (i < (unsigned)(w >> 32)) return (int)__ldcg(&a.worklist[(size_t)(g & 3u) * a.cap + i]);
         if (ld_volatile_u32(&S->gen) == g) return TILE_NEXT_GEN;
         s_gen = g + 1u;
       }
@@ -645,6 +645,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     // Thread 0 does it in steps spread over its column phase, each consuming what the previous one asked
     // for, so that no atomic, load or copy is ever waited for.
     unsigned pop_i = 0, pop_g = 0, pop_c = 0;
+    unsigned long long pop_w = 0;
     int next_tile = TILE_NONE;
     const bool build_now = build_next;  // (feeder thread) the tile staged last time was the list's trigger entry
     build_next = false;
@@ -704,11 +705,9 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (build_now) {
               if (g == h2) stage_tile(q ^ 1, TILE_BUILD);
             } else {
-            if (g == h0) {
-              pop_i = atomicAdd(&S->gcursor[pop_g & 3u], 1u);
-              pop_c = ld_volatile_u32(&S->gcount[pop_g & 3u]);
-            }
+            if (g == h0) pop_w = atomicAdd(&S->gslot[pop_g & 3u], 1ull);
             if (g == h1) {
+              pop_i = (unsigned)pop_w; pop_c = (unsigned)(pop_w >> 32);
               // the entry `lookahead` before the list's end is the trigger: whoever pops it builds the next
               // generation right after that tile, so that the new list is out when this one runs dry
               // (short lists: not before the fraction trig_q8/256 of the list is handed out)
@@ -720,8 +719,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
                 // from it right here (the CTA then never leaves its pipeline); else the CTA goes to the switch
                 pop_g += 1u;
                 s_gen = pop_g;
-                pop_i = atomicAdd(&S->gcursor[pop_g & 3u], 1u);
-                pop_c = ld_volatile_u32(&S->gcount[pop_g & 3u]);
+                pop_w = atomicAdd(&S->gslot[pop_g & 3u], 1ull);
+                pop_i = (unsigned)pop_w; pop_c = (unsigned)(pop_w >> 32);
               }
               next_tile = (pop_i < pop_c) ? (int)__ldcg(&a.worklist[(size_t)(pop_g & 3u) * a.cap + pop_i]) : TILE_NEXT_GEN;
             }
@@ -1297,6 +1296,12 @@ cudaError_t launch_relax_persistent(const TiledLaunch& tl, const CUtensorMap& tm
                                     const RelaxArgs& a, cudaStream_t stream) {
   return launch_relax_any(tl, tm_slow, tm_tt, a, true, stream);
 }
+// after a single-launch solve: fold every key that is still pending into kmin_bits (must stay INF)
+cudaError_t launch_persist_check(const RelaxArgs& a, cudaStream_t stream) {
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  scan_min_key<<<(unsigned)std::min<size_t>(296, (total + 255) / 256), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
 size_t tiled_persistent_max_keys(int rxy) {  // the generation builder caches every key in the idle TMA ring
   switch (rxy) {
     case 2: return 4 * (size_t)TileDims<2>::BOX_STRIDE;
@@ -1313,7 +1318,7 @@ __global__ void persist_begin_kernel(const RelaxArgs a) {
   if (threadIdx.x == 0) {
     S->gen = 0u; S->builder = 0u; S->done = 0u;
     S->inflight = cnt;
-    S->gcount[0] = cnt; S->gcursor[0] = 0u;
+    S->gslot[0] = (unsigned long long)cnt << 32;
   }
 }
 cudaError_t launch_persist_begin(const RelaxArgs& a, cudaStream_t stream) {

@@ -67,6 +67,7 @@ cudaError_t launch_relax_tiled(const TiledLaunch& tl, const CUtensorMap& tm_slow
 cudaError_t launch_relax_persistent(const TiledLaunch& tl, const CUtensorMap& tm_slow, const CUtensorMap& tm_tt,
                                     const RelaxArgs& a, cudaStream_t stream);
 cudaError_t launch_persist_begin(const RelaxArgs& a, cudaStream_t stream);
+cudaError_t launch_persist_check(const RelaxArgs& a, cudaStream_t stream);
 size_t tiled_persistent_max_keys(int rxy);
 // Two launches: (1) min-reduce the activation keys, (2) move every tile whose key is within the
 // bucket of that minimum to the next work list (clearing its key), flip parity, advance the

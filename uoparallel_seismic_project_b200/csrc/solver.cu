@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -32,6 +33,7 @@
 using namespace sweeptt;
 
 static constexpr int MAX_GROUPS = 8;
+static constexpr int STATE_SLOTS = 1 + 512;  // slot 0: the whole-context view; 1..: one per slice of the solve plan
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -166,7 +168,12 @@ struct sweeptt_ctx {
   TiledLaunch tl{};
   CUtensorMap tm_slow{}, tm_tt{};
   bool maps_valid = false;
-  int consts_rxy = -1;  // variant the __constant__ tables were built for
+  int consts_rxy = -1;  // variant the host image of the __constant__ tables was built for
+  std::vector<ColumnDev> img_cols;
+  std::vector<float> img_hd;
+  std::vector<ExtraDev> img_extra;
+  std::vector<uint2> img_pdesc;
+  uint64_t img_sig = 0;
   std::vector<int> pat_begin;  // column ranges per k-pattern (stock-star kernels)
   std::vector<unsigned short> psplit;  // per pattern group: first column of every fine part (kernels.cu c_psplit)
   std::vector<PullColumn> dev_columns;  // pattern-sorted, even-padded columns as uploaded
@@ -174,20 +181,34 @@ struct sweeptt_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
 
-  // Source groups (graph loop only): the sources are split into G groups that run as G
-  // independent WHILE graphs on G streams over disjoint slices of the work lists / keys / boxes.
-  // One group's relaxation CTAs fill the SMs that another group's round has already drained, so
-  // the per-round tail (work-list length not a multiple of the SM count) is hidden.
-  struct Group {
+  // Solve plan: the sources are cut into WAVES that run one after the other; a wave is either ONE slice solved by
+  // a single persistent launch (all its activation keys fit the CTA's shared memory: the best scheduler), or G
+  // slices ("source groups") that run as G independent WHILE graphs on G streams -- one group's relaxation CTAs
+  // fill the SMs that another group's round has already drained.  Every slice works on its own part of the work
+  // lists / keys / boxes and has its own SolveState slot, so a whole solve is enqueued without a host decision
+  // and finished sources can leave for the host while later waves are still being relaxed (sweeptt_solve).
+  struct Slice {
+    int wave = 0;
     int s0 = 0, ns = 0;
-    cudaStream_t stream = nullptr;  // null: the context's own stream
-    cudaEvent_t done = nullptr;
+    int slot = 1;                   // SolveState slot
+    int lane = 0;                   // stream: 0 = the context's own, g >= 1 = aux_streams[g-1]
+    bool persistent = false;
     cudaGraphExec_t graph = nullptr;
     CUtensorMap tm_tt{};
   };
-  std::vector<Group> groups;
-  bool groups_valid = false;
+  std::vector<Slice> plan;
+  int plan_waves = 0;
+  bool plan_valid = false;
+  std::vector<cudaStream_t> aux_streams;
+  std::vector<cudaEvent_t> aux_done;
   cudaEvent_t ev_fork = nullptr;
+
+  // host <-> device staging of sweeptt_solve: finished boxes are un-padded into a ring of dense boxes on the solve
+  // stream and copied out by the copy stream while the next wave is being relaxed
+  cudaStream_t copy_stream = nullptr;
+  float* d_out_ring = nullptr;
+  size_t out_ring_boxes = 0, out_ring_box_floats = 0;
+  std::vector<cudaEvent_t> ring_unpadded, ring_copied;
 
   std::vector<cudaEvent_t> prof_events;
   bool allow_outside_sources = false;  // slab contexts: the start may lie in another slab
@@ -195,20 +216,55 @@ struct sweeptt_ctx {
   int force_window_axis = -1;          // slab contexts: all slabs must share one axis order
 };
 
-// the __constant__ star tables are per-device module state: remember which context owns them
-static std::mutex g_const_mu;
-static std::map<int, sweeptt_ctx*> g_const_owner;
-static std::map<int, uint64_t> g_const_sig;  // content hash of the tables currently in __constant__ memory
+// The __constant__ star tables are per-device module state shared by every context on that device.  A compute
+// call holds a LEASE on them for its whole duration: contexts whose tables are identical (slab contexts, the
+// cached contexts of sweeptt_solve) share the lease, a context with a different star waits until the device's
+// tables are unused, then replaces them.  So two host threads driving different stars on one device serialise
+// instead of overwriting each other's tables (include/sweeptt.h, "Threading").
+namespace {
+struct ConstTables {
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t sig = 0;
+  bool loaded = false;
+  int users = 0;
+};
+ConstTables& const_tables(int device) {
+  static std::mutex mu;
+  static std::map<int, ConstTables*> all;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = all.find(device);
+  if (it == all.end()) it = all.emplace(device, new ConstTables()).first;
+  return *it->second;
+}
+struct ConstLease {
+  ConstTables* t = nullptr;
+  ConstLease() = default;
+  ConstLease(const ConstLease&) = delete;
+  ConstLease& operator=(const ConstLease&) = delete;
+  void release() {
+    if (!t) return;
+    {
+      std::lock_guard<std::mutex> lk(t->mu);
+      --t->users;
+    }
+    t->cv.notify_all();
+    t = nullptr;
+  }
+  ~ConstLease() { release(); }
+};
+}  // namespace
 
 static void invalidate_graph(sweeptt_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   c->graph_exec = nullptr;
   c->graph_valid = false;
-  for (auto& g : c->groups) {
-    if (g.graph) cudaGraphExecDestroy(g.graph);
-    g.graph = nullptr;
+  for (auto& sl : c->plan) {
+    if (sl.graph) cudaGraphExecDestroy(sl.graph);
+    sl.graph = nullptr;
   }
-  c->groups_valid = false;
+  c->plan.clear();
+  c->plan_valid = false;
 }
 
 static int dev_alloc(sweeptt_ctx* c, void** p, size_t bytes) {
@@ -254,8 +310,8 @@ extern "C" sweeptt_ctx* sweeptt_create(const sweeptt_opts* opts) {
   c->own_stream = true;
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
        cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
-       cudaMallocHost(&c->h_state, sizeof(SolveState) * (1 + MAX_GROUPS)) == cudaSuccess &&
+  ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState) * STATE_SLOTS) == cudaSuccess &&
+       cudaMallocHost(&c->h_state, sizeof(SolveState) * STATE_SLOTS) == cudaSuccess &&
        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
        cudaMalloc(&c->d_viol, 32) == cudaSuccess;
   if (!ok) {
@@ -270,16 +326,13 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  {
-    std::lock_guard<std::mutex> lk(g_const_mu);
-    auto it = g_const_owner.find(c->device);
-    if (it != g_const_owner.end() && it->second == c) { g_const_owner.erase(it); g_const_sig.erase(c->device); }
-  }
   invalidate_graph(c);
-  for (auto& g : c->groups) {
-    if (g.stream) cudaStreamDestroy(g.stream);
-    if (g.done) cudaEventDestroy(g.done);
-  }
+  for (auto st : c->aux_streams) cudaStreamDestroy(st);
+  for (auto e : c->aux_done) cudaEventDestroy(e);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (auto e : c->ring_unpadded) cudaEventDestroy(e);
+  for (auto e : c->ring_copied) cudaEventDestroy(e);
+  cudaFree(c->d_out_ring);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
@@ -580,16 +633,17 @@ static int choose_kernel(sweeptt_ctx* c) {
   return 1;
 }
 
-static int upload_constants(sweeptt_ctx* c) {
-  std::lock_guard<std::mutex> lk(g_const_mu);
-  auto it = g_const_owner.find(c->device);
-  if (it != g_const_owner.end() && it->second == c && c->consts_rxy == c->tl.rxy) return 1;
+// Host image of the context's __constant__ tables (rebuilt after set_star / a kernel change) and its content hash.
+static int build_const_image(sweeptt_ctx* c) {
+  if (c->consts_rxy == c->tl.rxy) return 1;
   int sxd, syd, szd;
   tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
   // columns in upload order (pattern-sorted, even-padded); half-distances re-packed in the same
   // order so that a pattern group's hd values are contiguous; two spare entries at the end
-  std::vector<ColumnDev> cols(c->dev_columns.size() + 2);
-  std::vector<float> hd_packed;
+  std::vector<ColumnDev>& cols = c->img_cols;
+  std::vector<float>& hd_packed = c->img_hd;
+  cols.assign(c->dev_columns.size() + 2, ColumnDev{});
+  hd_packed.clear();
   for (size_t i = 0; i < c->dev_columns.size(); ++i) {
     const PullColumn& pc = c->dev_columns[i];
     ColumnDev d;
@@ -608,22 +662,15 @@ static int upload_constants(sweeptt_ctx* c) {
   cols[cols.size() - 2] = cols[cols.size() - 1] = cols[c->dev_columns.size() - 1];
   if ((int)hd_packed.size() > MAX_COL_HD || (int)cols.size() > MAX_COLUMNS)
     return fail("star tables exceed the __constant__ budget (%zu half-distances, %zu columns)", hd_packed.size(), cols.size());
-  std::vector<ExtraDev> ex(c->star.extra.size());
+  std::vector<ExtraDev>& ex = c->img_extra;
+  ex.assign(c->star.extra.size(), ExtraDev{});
   for (size_t i = 0; i < ex.size(); ++i) {
     const PullOffset& p = c->star.extra[i];
     ex[i] = ExtraDev{p.i, p.j, p.k, p.i * syd * szd + p.j * szd + p.k, p.hd, p.guarded, 0, 0};
   }
-  // identical tables already resident (e.g. several slab contexts sharing one device)?
-  uint64_t sig = 1469598103934665603ull;
-  auto mix = [&sig](const void* p, size_t n) {
-    const unsigned char* b = static_cast<const unsigned char*>(p);
-    for (size_t i = 0; i < n; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
-  };
-  mix(cols.data(), cols.size() * sizeof(ColumnDev));
-  mix(hd_packed.data(), hd_packed.size() * sizeof(float));
-  mix(ex.data(), ex.size() * sizeof(ExtraDev));
   // per (table, group, part): the part's piece of the group + where its half-distances start (kernels.cu c_pdesc)
-  std::vector<uint2> pdesc((size_t)6 * MAX_PATTERNS * MAX_WARPS, make_uint2(0u, 0u));
+  std::vector<uint2>& pdesc = c->img_pdesc;
+  pdesc.assign((size_t)6 * MAX_PATTERNS * MAX_WARPS, make_uint2(0u, 0u));
   for (int table = 0; table < 6; ++table)
     for (int g = 0; g + 1 < (int)c->pat_begin.size() && g < MAX_PATTERNS; ++g)
       for (int pt = 0; pt < MAX_WARPS; ++pt) {
@@ -632,21 +679,41 @@ static int upload_constants(sweeptt_ctx* c) {
         pdesc[((size_t)table * MAX_PATTERNS + g) * MAX_WARPS + pt] =
             make_uint2(lo | (hi << 16), lo < hi ? (unsigned)cols[lo].hd_begin : 0u);
       }
+  uint64_t sig = 1469598103934665603ull;
+  auto mix = [&sig](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
+  };
+  mix(cols.data(), cols.size() * sizeof(ColumnDev));
+  mix(hd_packed.data(), hd_packed.size() * sizeof(float));
+  mix(ex.data(), ex.size() * sizeof(ExtraDev));
   mix(pdesc.data(), pdesc.size() * sizeof(uint2));
-  auto sg = g_const_sig.find(c->device);
-  if (sg != g_const_sig.end() && sg->second == sig && it != g_const_owner.end()) {
-    g_const_owner[c->device] = c;
-    c->consts_rxy = c->tl.rxy;
-    return 1;
-  }
-  g_const_sig[c->device] = sig;
-  // a different context may still be running with the old tables on another stream
-  if (it != g_const_owner.end() && it->second != c) CK(cudaDeviceSynchronize());
-  CK(upload_star_constants(cols.data(), (int)cols.size(), hd_packed.data(), (int)hd_packed.size(), ex.data(),
-                           (int)ex.size(), pdesc.data(), (int)pdesc.size(), c->stream));
-  CK(cudaStreamSynchronize(c->stream));  // host vectors die here
-  g_const_owner[c->device] = c;
+  c->img_sig = sig | 1ull;
   c->consts_rxy = c->tl.rxy;
+  return 1;
+}
+
+// Takes the lease on the device's __constant__ tables for this context's star (uploading them if others are there).
+static int upload_constants(sweeptt_ctx* c, ConstLease* lease) {
+  if (!build_const_image(c)) return 0;
+  if (lease->t) return 1;  // (already held by this call)
+  ConstTables& t = const_tables(c->device);
+  std::unique_lock<std::mutex> lk(t.mu);
+  t.cv.wait(lk, [&] { return t.users == 0 || (t.loaded && t.sig == c->img_sig); });
+  if (!(t.loaded && t.sig == c->img_sig)) {
+    // nobody holds the old tables; their last kernels were synchronised by the calls that launched them, but a
+    // caller-provided stream may still be draining
+    CK(cudaDeviceSynchronize());
+    t.loaded = false;
+    CK(upload_star_constants(c->img_cols.data(), (int)c->img_cols.size(), c->img_hd.data(), (int)c->img_hd.size(),
+                             c->img_extra.data(), (int)c->img_extra.size(), c->img_pdesc.data(), (int)c->img_pdesc.size(),
+                             c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    t.sig = c->img_sig;
+    t.loaded = true;
+  }
+  ++t.users;
+  lease->t = &t;
   return 1;
 }
 
@@ -790,13 +857,13 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   return a;
 }
 
-static int ready(sweeptt_ctx* c) {
+static int ready(sweeptt_ctx* c, ConstLease* lease) {
   if (!c) return fail("null context");
   if (!c->have_model || !c->have_star || !c->have_sources) return fail("context needs a model, a star and start points first");
   CK(cudaSetDevice(c->device));
   if (c->kernel_used == SWEEPTT_KERNEL_TILED) {
     if (!build_maps(c)) return 0;
-    if (!upload_constants(c)) return 0;
+    if (!upload_constants(c, lease)) return 0;
     // activation bucket = factor x (delay of the longest star edge in a medium of mean slowness)
     double factor = 2.0;  // measured on config 2: 1 -> 21.9 ms, 2 -> 21.2 ms, 4 -> 21.4 ms, off -> 50 ms
     if (const char* e = getenv("SWEEPTT_BUCKET")) factor = atof(e);
@@ -816,7 +883,8 @@ static int ready(sweeptt_ctx* c) {
 }
 
 extern "C" int sweeptt_reset(sweeptt_ctx* c) {
-  if (!ready(c)) return 0;
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
   CK(launch_reset(make_args(c), c->opts.max_rounds, c->stream));
   return 1;
 }
@@ -876,47 +944,107 @@ static int build_graph(sweeptt_ctx* c) {
   return 1;
 }
 
-// slice of the context that group g works on
-static RelaxArgs group_args(sweeptt_ctx* c, int g) {
+// the part of the context that a slice of the solve plan works on
+static RelaxArgs slice_args(sweeptt_ctx* c, const sweeptt_ctx::Slice& sl) {
   RelaxArgs a = make_args(c);
-  const sweeptt_ctx::Group& G = c->groups[g];
   const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
-  a.tt = c->d_tt + (size_t)G.s0 * c->g.vol;
-  a.nsrc = G.ns;
-  a.src_xyz = c->d_src + 3 * G.s0;
-  a.st = c->d_state + 1 + g;
-  a.cap = (unsigned)(ntiles * G.ns);
-  a.worklist = c->d_worklist + 2 * ntiles * G.s0;  // each group owns 2*cap consecutive entries
-  a.key = c->d_key + ntiles * G.s0;
-  if (a.tmax) a.tmax = c->d_tmax + ntiles * G.s0;
+  a.tt = c->d_tt + (size_t)sl.s0 * c->g.vol;
+  a.nsrc = sl.ns;
+  a.src_xyz = c->d_src + 3 * sl.s0;
+  a.st = c->d_state + sl.slot;
+  a.cap = (unsigned)(ntiles * sl.ns);
+  a.worklist = c->d_worklist + 4 * ntiles * sl.s0;  // each slice owns 4*cap consecutive entries
+  a.key = c->d_key + ntiles * sl.s0;
+  a.busy = c->d_busy + ntiles * sl.s0;
+  a.keysnap = c->d_keysnap + ntiles * sl.s0;
+  if (a.tmax) a.tmax = c->d_tmax + ntiles * sl.s0;
   return a;
 }
 
-static int build_groups(sweeptt_ctx* c, int want) {
-  if (c->groups_valid && (int)c->groups.size() == want) return 1;
-  for (auto& g : c->groups)
-    if (g.graph) { cudaGraphExecDestroy(g.graph); g.graph = nullptr; }
-  while ((int)c->groups.size() > want) {
-    auto& g = c->groups.back();
-    if (g.stream) cudaStreamDestroy(g.stream);
-    if (g.done) cudaEventDestroy(g.done);
-    c->groups.pop_back();
+static int env_loop(const sweeptt_ctx* c) {
+  int loop = c->opts.loop;
+  if (const char* env = getenv("SWEEPTT_LOOP")) {
+    if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
+    if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
   }
-  while ((int)c->groups.size() < want) {
-    sweeptt_ctx::Group g;
-    if (!c->groups.empty()) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
-    c->groups.push_back(g);
+  return loop;
+}
+
+// How many sources ONE persistent launch can take (0: the single-launch scheduler is not used).
+static int persistent_capacity(sweeptt_ctx* c) {
+  if (c->kernel_used != SWEEPTT_KERNEL_TILED || c->opts.max_rounds > 0) return 0;
+  // the 3-FS kernel (three 4-warp CTAs per SM, tiles of a few hundred nanoseconds) spends its time in list
+  // switches: measured 4.6 ms against 2.8 ms for the graph of rounds (config 1) -- unless asked for explicitly
+  if (c->tl.nw < MAX_WARPS && !getenv("SWEEPTT_PERSIST")) return 0;
+  if (const char* e = getenv("SWEEPTT_PERSIST")) { if (atoi(e) == 0) return 0; }
+  if (env_loop(c) == SWEEPTT_LOOP_BATCHED) return 0;
+  // One CTA builds every list.  While all keys fit its idle TMA ring (53 Ki keys for 818-FS: 8 sources on a
+  // 241x241x51 box) a build takes a few microseconds and hides behind the early-build lookahead; with a
+  // snapshot in global memory it does not (measured: 16 sources 65 ms against 50 ms for the graph of rounds).
+  // More sources than that run as consecutive waves of persistent launches (build_plan).
+  size_t max_keys = tiled_persistent_max_keys(c->tl.rxy);
+  if (const char* e = getenv("SWEEPTT_PERSIST_MAX_KEYS")) max_keys = (size_t)atoll(e);
+  const size_t ntiles = (size_t)c->g.ntx * c->g.nty * c->g.ntz;
+  return (int)std::min<size_t>(max_keys / ntiles, 1u << 20);
+}
+
+// Cut the sources into waves and slices (sweeptt_ctx::Slice) and prepare each slice's tensor map / graph.
+static int build_plan(sweeptt_ctx* c) {
+  if (c->plan_valid) return 1;
+  invalidate_graph(c);
+  const int cap = persistent_capacity(c);
+  int wave_size = 0;  // sources per wave
+  bool persistent = false;
+  if (cap >= 1) {
+    // balanced waves of at most `cap` sources, e.g. 111 sources -> 14 waves of 8 (the last one 7)
+    const int nwaves = (c->nsrc + cap - 1) / cap;
+    wave_size = (c->nsrc + nwaves - 1) / nwaves;
+    persistent = true;
   }
-  for (int g = 0; g < want; ++g) {
-    auto& G = c->groups[g];
-    G.s0 = (int)((long long)c->nsrc * g / want);
-    G.ns = (int)((long long)c->nsrc * (g + 1) / want) - G.s0;
-    if (c->kernel_used == SWEEPTT_KERNEL_TILED && !encode_tt_map(c, c->d_tt + (size_t)G.s0 * c->g.vol, G.ns, &G.tm_tt)) return 0;
-    cudaStream_t st = G.stream ? G.stream : c->stream;
-    if (!build_while_graph(c, group_args(c, g), G.tm_tt, st, &G.graph)) return 0;
+  if (const char* e = getenv("SWEEPTT_WAVE")) {  // 0: every source in ONE wave of graph groups (the round-1 scheme)
+    const int w = atoi(e);
+    if (w <= 0) { wave_size = c->nsrc; persistent = cap >= c->nsrc; }
+    else { wave_size = std::min(w, c->nsrc); persistent = cap >= wave_size; }
   }
-  c->groups_valid = true;
+  if (wave_size <= 0) wave_size = c->nsrc;
+  int want_groups = 2;
+  if (const char* env = getenv("SWEEPTT_GROUPS")) want_groups = atoi(env);
+  want_groups = std::max(1, std::min(want_groups, MAX_GROUPS));
+  int slot = 1, wave = 0;
+  for (int s0 = 0; s0 < c->nsrc; s0 += wave_size, ++wave) {
+    const int ns = std::min(wave_size, c->nsrc - s0);
+    const int parts = persistent ? 1 : std::min(want_groups, ns);
+    for (int g = 0; g < parts; ++g) {
+      sweeptt_ctx::Slice sl;
+      sl.wave = wave;
+      sl.s0 = s0 + (int)((long long)ns * g / parts);
+      sl.ns = s0 + (int)((long long)ns * (g + 1) / parts) - sl.s0;
+      sl.slot = slot++;
+      sl.lane = g;
+      sl.persistent = persistent;
+      if (slot > STATE_SLOTS) return fail("too many slices in the solve plan (%d sources in waves of %d)", c->nsrc, wave_size);
+      c->plan.push_back(sl);
+    }
+  }
+  c->plan_waves = wave;
+  int lanes = 1;
+  for (const auto& sl : c->plan) lanes = std::max(lanes, sl.lane + 1);
+  while ((int)c->aux_streams.size() < lanes - 1) {
+    cudaStream_t st;
+    cudaEvent_t ev;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->aux_streams.push_back(st);
+    c->aux_done.push_back(ev);
+  }
+  for (auto& sl : c->plan) {
+    if (c->kernel_used == SWEEPTT_KERNEL_TILED && !encode_tt_map(c, c->d_tt + (size_t)sl.s0 * c->g.vol, sl.ns, &sl.tm_tt)) return 0;
+    if (!sl.persistent) {
+      cudaStream_t st = sl.lane ? c->aux_streams[sl.lane - 1] : c->stream;
+      if (!build_while_graph(c, slice_args(c, sl), sl.tm_tt, st, &sl.graph)) return 0;
+    }
+  }
+  c->plan_valid = true;
   return 1;
 }
 
@@ -1012,49 +1140,93 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
   return 1;
 }
 
-// G concurrent source groups, each its own device-resident WHILE graph (see sweeptt_ctx::Group)
-static int run_groups(sweeptt_ctx* c, int want, sweeptt_stats* stats) {
-  if (!build_groups(c, want)) return 0;
+// Runs the solve plan: every wave is enqueued without waiting for the one before it; `after_wave(s0, ns)` (may be
+// empty) is called as soon as a wave's work is on the context's stream -- whatever it enqueues there runs when the
+// wave's sources have converged (sweeptt_solve un-pads them and sends them to the host while the next wave runs).
+static int run_plan(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int)>& after_wave) {
+  if (!build_plan(c)) return 0;
+  const bool profile = c->opts.profile_kernels != 0;  // (persistent waves only: run_plan is not used otherwise)
+  size_t ev_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
-  CK(cudaEventRecord(c->ev_fork, c->stream));
-  for (int g = 0; g < want; ++g) {
-    auto& G = c->groups[g];
-    cudaStream_t st = G.stream ? G.stream : c->stream;
-    if (G.stream) CK(cudaStreamWaitEvent(G.stream, c->ev_fork, 0));
-    CK(launch_reset(group_args(c, g), c->opts.max_rounds, st));
-    CK(cudaGraphLaunch(G.graph, st));
-    if (G.stream) {
-      CK(cudaEventRecord(G.done, G.stream));
+  size_t i = 0;
+  while (i < c->plan.size()) {
+    const int wave = c->plan[i].wave;
+    size_t j = i;
+    while (j < c->plan.size() && c->plan[j].wave == wave) ++j;
+    if (j - i > 1) CK(cudaEventRecord(c->ev_fork, c->stream));
+    for (size_t k = i; k < j; ++k) {
+      const auto& sl = c->plan[k];
+      cudaStream_t st = sl.lane ? c->aux_streams[sl.lane - 1] : c->stream;
+      if (sl.lane) CK(cudaStreamWaitEvent(st, c->ev_fork, 0));
+      const RelaxArgs a = slice_args(c, sl);
+      CK(launch_reset(a, c->opts.max_rounds, st));
+      if (sl.persistent) {
+        CK(launch_persist_begin(a, st));
+        if (profile) {
+          while (c->prof_events.size() < ev_used + 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            c->prof_events.push_back(e);
+          }
+          CK(cudaEventRecord(c->prof_events[ev_used], st));
+        }
+        CK(launch_relax_persistent(c->tl, c->tm_slow, sl.tm_tt, a, st));
+        if (profile) { CK(cudaEventRecord(c->prof_events[ev_used + 1], st)); ev_used += 2; }
+        CK(launch_persist_check(a, st));  // any key still pending after "done" -> kmin_bits != INF (read below)
+      } else {
+        CK(cudaGraphLaunch(sl.graph, st));
+      }
+      if (sl.lane) CK(cudaEventRecord(c->aux_done[sl.lane - 1], st));
     }
-  }
-  for (int g = 0; g < want; ++g)
-    if (c->groups[g].stream) CK(cudaStreamWaitEvent(c->stream, c->groups[g].done, 0));
-  // the single-group view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
-  {
-    RelaxArgs whole = make_args(c);
-    CK(launch_reset_state_only(whole.st, c->opts.max_rounds, c->stream));
+    for (size_t k = i; k < j; ++k)
+      if (c->plan[k].lane) CK(cudaStreamWaitEvent(c->stream, c->aux_done[c->plan[k].lane - 1], 0));
+    if (after_wave) {
+      const int s0 = c->plan[i].s0, s1 = c->plan[j - 1].s0 + c->plan[j - 1].ns;
+      if (!after_wave(s0, s1 - s0)) return 0;
+    }
+    i = j;
   }
   CK(cudaEventRecord(c->ev1, c->stream));
-  CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState) * (1 + want), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaEventSynchronize(c->ev1));
+  const size_t nslots = 1 + c->plan.size();
+  CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState) * nslots, cudaMemcpyDeviceToHost, c->stream));
+  // the round-based view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
+  CK(launch_reset_state_only(c->d_state, c->opts.max_rounds, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  int pending = 0;
   if (stats) {
     std::memset(stats, 0, sizeof *stats);
     stats->struct_size = sizeof *stats;
     stats->kernel_used = c->kernel_used;
     stats->devices_used = 1;
     stats->solve_ms = ms;
+    for (size_t e = 0; e < ev_used; e += 2) {
+      float k = 0;
+      CK(cudaEventElapsedTime(&k, c->prof_events[e], c->prof_events[e + 1]));
+      stats->relax_kernel_ms += k;
+    }
   }
-  for (int g = 0; g < want; ++g) {
-    const SolveState& h = c->h_state[1 + g];
-    pending |= (c->kernel_used == SWEEPTT_KERNEL_TILED) ? (h.count[h.parity] != 0) : (h.last_changed_round == h.round);
+  int pending = 0;
+  for (const auto& sl : c->plan) {
+    const SolveState& h = c->h_state[sl.slot];
+    if (sl.persistent) {
+      // done == 1 alone is not trusted: nothing may be in flight and no activation key may be left
+      if (h.done != 1u || h.inflight != 0u || h.kmin_bits != 0x7f800000u)
+        return fail("single-launch solve of sources %d..%d stopped without reaching the fixed point (done %u, in flight %u, "
+                    "pending key %08x)", sl.s0, sl.s0 + sl.ns - 1, h.done, h.inflight, h.kmin_bits);
+    } else {
+      pending |= (c->kernel_used == SWEEPTT_KERNEL_TILED) ? (h.count[h.parity] != 0) : (h.last_changed_round == h.round);
+    }
     if (stats) {
+      const long long per_reset = (c->kernel_used == SWEEPTT_KERNEL_TILED && make_args(c).tmax) ? 5 : 4;  // state, tt, keys, (tmax,) sources
       stats->rounds = std::max(stats->rounds, h.round);
-      stats->kernel_launches += (c->kernel_used == SWEEPTT_KERNEL_TILED ? 3LL : 2LL) * h.round + 4;
-      stats->relax_launches += h.round;
+      if (sl.persistent) {
+        stats->kernel_launches += per_reset + 3;  // + list 0, the solve itself, the final key scan
+        stats->relax_launches += 1;
+      } else {
+        stats->kernel_launches += (c->kernel_used == SWEEPTT_KERNEL_TILED ? 3LL : 2LL) * h.round + per_reset;
+        stats->relax_launches += h.round;
+      }
       stats->tile_visits += (long long)h.tile_visits;
       stats->relaxations += (long long)h.pulls;
       stats->units_run += (long long)h.units_run;
@@ -1065,66 +1237,22 @@ static int run_groups(sweeptt_ctx* c, int want, sweeptt_stats* stats) {
   return 1;
 }
 
-// Single-launch solve (kernels.cu, relax_tiled<..., PERSIST>): reset, one persistent launch, read the state.
-static bool persistent_eligible(sweeptt_ctx* c) {
-  if (c->kernel_used != SWEEPTT_KERNEL_TILED || c->opts.max_rounds > 0) return false;
-  // the 3-FS kernel (three 4-warp CTAs per SM, tiles of a few hundred nanoseconds) spends its time in list
-  // switches: measured 4.6 ms against 2.8 ms for the graph of rounds (config 1) -- unless asked for explicitly
-  if (c->tl.nw < MAX_WARPS && !getenv("SWEEPTT_PERSIST")) return false;
-  if (const char* e = getenv("SWEEPTT_PERSIST")) { if (atoi(e) == 0) return false; }
-  int loop = c->opts.loop;
-  if (const char* env = getenv("SWEEPTT_LOOP")) {
-    if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
-    if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
-  }
+// Is the device-resident solve plan usable (else: the host-polled loop over all sources at once)?
+static bool plan_usable(sweeptt_ctx* c) {
+  const int loop = env_loop(c);
   if (loop == SWEEPTT_LOOP_BATCHED) return false;
-  // One CTA builds every list.  While all keys fit its idle TMA ring (53 Ki keys for 818-FS: 8 sources on a
-  // 241x241x51 box) a build takes a few microseconds and hides behind the early-build lookahead; with a
-  // snapshot in global memory it does not (measured: 16 sources 65 ms against 50 ms for the graph of rounds,
-  // whose compaction runs on the whole device and whose launches are long enough to make tails irrelevant).
-  size_t max_keys = tiled_persistent_max_keys(c->tl.rxy);
-  if (const char* e = getenv("SWEEPTT_PERSIST_MAX_KEYS")) max_keys = (size_t)atoll(e);
-  const size_t keys = (size_t)c->nsrc * c->g.ntx * c->g.nty * c->g.ntz;
-  return keys <= max_keys;
-}
-static int run_persistent(sweeptt_ctx* c, sweeptt_stats* stats) {
-  const RelaxArgs a = make_args(c);
-  CK(cudaEventRecord(c->ev0, c->stream));
-  CK(launch_reset(a, 0, c->stream));
-  CK(launch_persist_begin(a, c->stream));
-  CK(cudaEventRecord(c->ev2, c->stream));
-  CK(launch_relax_persistent(c->tl, c->tm_slow, c->tm_tt, a, c->stream));
-  CK(cudaEventRecord(c->ev1, c->stream));
-  if (!read_state(c)) return 0;
-  CK(cudaEventSynchronize(c->ev1));
-  float ms = 0, kms = 0;
-  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  CK(cudaEventElapsedTime(&kms, c->ev2, c->ev1));
-  const SolveState& h = *c->h_state;
-  fill_stats(c, stats, 0, a.tmax ? 7 : 6, 1, kms);  // reset (state, tt, keys, tmax, sources) + list 0 + the solve itself
-  if (stats) stats->solve_ms = ms;
-  if (h.done != 1u) return fail("single-launch solve stopped without reaching the fixed point (state %u)", h.done);
-  // the round-based view of the state (sweeptt_step / put_tt) restarts from "nothing pending"
-  CK(launch_reset_state_only(a.st, c->opts.max_rounds, c->stream));
-  return 1;
+  if (c->opts.profile_kernels) {  // per-launch timing: only the single-launch waves can be bracketed from outside
+    const int cap = persistent_capacity(c);
+    if (cap < 1) return false;
+    if (const char* e = getenv("SWEEPTT_WAVE")) { const int w = atoi(e); if (w <= 0 ? cap < c->nsrc : cap < std::min(w, c->nsrc)) return false; }
+    return true;
+  }
+  return true;
 }
 
-extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
-  if (!ready(c)) return 0;
+static int run_locked(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int)>& after_wave) {
   if (stats) { std::memset(stats, 0, sizeof *stats); }
-  if (persistent_eligible(c)) return run_persistent(c, stats);
-  {
-    int loop = c->opts.loop;
-    if (const char* env = getenv("SWEEPTT_LOOP")) {
-      if (!strcmp(env, "graph")) loop = SWEEPTT_LOOP_GRAPH;
-      if (!strcmp(env, "batched")) loop = SWEEPTT_LOOP_BATCHED;
-    }
-    int want = 2;
-    if (const char* env = getenv("SWEEPTT_GROUPS")) want = atoi(env);
-    want = std::max(1, std::min({want, c->nsrc, MAX_GROUPS}));
-    if ((loop == SWEEPTT_LOOP_AUTO || loop == SWEEPTT_LOOP_GRAPH) && !c->opts.profile_kernels && want > 1)
-      return run_groups(c, want, stats);
-  }
+  if (plan_usable(c)) return run_plan(c, stats, after_wave);
   CK(cudaEventRecord(c->ev0, c->stream));
   CK(launch_reset(make_args(c), c->opts.max_rounds, c->stream));
   int changed = 0;
@@ -1135,11 +1263,19 @@ extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   if (stats) { stats->solve_ms = ms; stats->kernel_launches += 4; }
   if (changed && c->opts.max_rounds > 0) return fail("not converged after max_rounds = %d rounds", c->opts.max_rounds);
+  if (after_wave && !after_wave(0, c->nsrc)) return 0;
   return 1;
 }
 
+extern "C" int sweeptt_run(sweeptt_ctx* c, sweeptt_stats* stats) {
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
+  return run_locked(c, stats, nullptr);
+}
+
 extern "C" int sweeptt_step(sweeptt_ctx* c, int rounds, int* changed, sweeptt_stats* stats) {
-  if (!ready(c)) return 0;
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
   if (rounds < 1) return fail("sweeptt_step: rounds must be >= 1");
   if (stats) std::memset(stats, 0, sizeof *stats);
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -1166,7 +1302,8 @@ extern "C" int sweeptt_get_tt(sweeptt_ctx* c, int s, float* out) {
 
 extern "C" int sweeptt_put_tt(sweeptt_ctx* c, int s, const float* in) {
   if (!c || !in) return fail("sweeptt_put_tt: null argument");
-  if (!ready(c)) return 0;
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
   if (s < 0 || s >= c->nsrc) return fail("sweeptt_put_tt: source %d out of range", s);
   const size_t dense = (size_t)c->g.nx * c->g.ny * c->g.nz;
   if (!ensure_stage(c, dense)) return 0;
@@ -1186,7 +1323,8 @@ extern "C" int sweeptt_put_tt(sweeptt_ctx* c, int s, const float* in) {
 }
 
 extern "C" int sweeptt_count_violations(sweeptt_ctx* c, int s, long long* violations) {
-  if (!ready(c)) return 0;
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
   if (s < 0 || s >= c->nsrc || !violations) return fail("sweeptt_count_violations: bad argument");
   CK(cudaMemsetAsync(c->d_viol, 0, 8, c->stream));
   CK(launch_count_violations(make_args(c), s, c->d_star, c->nstar, c->d_viol, c->stream));
@@ -1199,41 +1337,90 @@ extern "C" int sweeptt_count_violations(sweeptt_ctx* c, int s, long long* violat
 
 extern "C" long long sweeptt_relaxations_per_round(sweeptt_ctx* c) { return c ? c->pulls_per_round : 0; }
 extern "C" size_t sweeptt_pool_bytes(sweeptt_ctx* c) { return c ? c->pool_bytes : 0; }
+extern "C" long long sweeptt_tiles_per_source(sweeptt_ctx* c) {
+  return (c && c->have_model) ? (long long)c->g.ntx * c->g.nty * c->g.ntz : 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // one-shot solve + multi-start dispatcher
 // ---------------------------------------------------------------------------------------
 static std::mutex g_cache_mu;
-static std::map<int, sweeptt_ctx*> g_cache;
+namespace { struct CacheEntry; }
+extern "C" void sweeptt_release_cache(void);
+
+// The device's cached context, held exclusively for one sweeptt_solve call (two host threads calling
+// sweeptt_solve for the same device take turns)
+namespace {
+struct CacheEntry {
+  std::mutex busy;
+  sweeptt_ctx* ctx = nullptr;
+};
+std::map<int, CacheEntry*> g_cache_entries;
+struct CachedCtx {
+  CacheEntry* e = nullptr;
+  sweeptt_ctx* ctx = nullptr;
+  CachedCtx(int device, const sweeptt_opts& o) {
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      auto it = g_cache_entries.find(device);
+      if (it == g_cache_entries.end()) it = g_cache_entries.emplace(device, new CacheEntry()).first;
+      e = it->second;
+    }
+    e->busy.lock();
+    if (e->ctx) {
+      sweeptt_ctx* c = e->ctx;
+      const bool star_opts_changed = c->opts.star_used != o.star_used || c->opts.kernel != o.kernel;
+      const bool plan_opts_changed = c->opts.loop != o.loop || c->opts.max_rounds != o.max_rounds ||
+                                     c->opts.profile_kernels != o.profile_kernels;
+      c->opts = o;
+      c->opts.device = device;
+      if (star_opts_changed) c->have_star = false;
+      if (plan_opts_changed) invalidate_graph(c);
+    } else {
+      sweeptt_opts oo = o;
+      oo.device = device;
+      e->ctx = sweeptt_create(&oo);
+    }
+    ctx = e->ctx;
+  }
+  ~CachedCtx() { if (e) e->busy.unlock(); }
+};
+}  // namespace
 
 extern "C" void sweeptt_release_cache(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  for (auto& kv : g_cache) sweeptt_destroy(kv.second);
-  g_cache.clear();
+  for (auto& kv : g_cache_entries) {
+    std::lock_guard<std::mutex> use(kv.second->busy);
+    if (kv.second->ctx) sweeptt_destroy(kv.second->ctx);
+    kv.second->ctx = nullptr;
+  }
 }
 
-static sweeptt_ctx* cached_ctx(int device, const sweeptt_opts& o) {
-  std::lock_guard<std::mutex> lk(g_cache_mu);
-  auto it = g_cache.find(device);
-  if (it != g_cache.end()) {
-    sweeptt_ctx* c = it->second;
-    const bool star_opts_changed = c->opts.star_used != o.star_used || c->opts.kernel != o.kernel;
-    c->opts = o;
-    c->opts.device = device;
-    if (star_opts_changed) c->have_star = false;
-    return c;
+// Ring of dense staging boxes for the way out: box s is un-padded on the solve stream (a few microseconds of SM
+// time behind the wave that produced it) and copied to the host by the copy stream while the next wave is relaxed.
+static int ensure_out_ring(sweeptt_ctx* c, size_t dense_floats, int want_boxes) {
+  size_t boxes = std::max<size_t>(2, std::min<size_t>((size_t)want_boxes, std::max<size_t>(2, (size_t(1) << 30) / (dense_floats * 4))));
+  if (c->out_ring_box_floats == dense_floats && c->out_ring_boxes >= boxes) return 1;
+  if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+  dev_free(c, c->d_out_ring, c->out_ring_boxes * c->out_ring_box_floats * 4);
+  c->d_out_ring = nullptr; c->out_ring_boxes = 0; c->out_ring_box_floats = 0;
+  if (!dev_alloc(c, (void**)&c->d_out_ring, boxes * dense_floats * 4)) return 0;
+  c->out_ring_boxes = boxes; c->out_ring_box_floats = dense_floats;
+  while (c->ring_unpadded.size() < boxes) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    c->ring_unpadded.push_back(a); c->ring_copied.push_back(b);
   }
-  sweeptt_opts oo = o;
-  oo.device = device;
-  sweeptt_ctx* c = sweeptt_create(&oo);
-  if (c) g_cache[device] = c;
-  return c;
+  if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  return 1;
 }
 
 static int solve_on_device(int device, const sweeptt_opts& o, const float* slowness, int nx, int ny, int nz,
                            const FS* fs, int starsize, const START* starts, int numstart, float* const* tt_out,
                            sweeptt_stats* st) {
-  sweeptt_ctx* c = cached_ctx(device, o);
+  CachedCtx cc(device, o);  // (exclusive use of the device's cached context for this call)
+  sweeptt_ctx* c = cc.ctx;
   if (!c) return 0;
   std::memset(st, 0, sizeof *st);
   CK(cudaSetDevice(device));
@@ -1247,21 +1434,37 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
                          std::memcmp(c->fs.data(), fs, sizeof(FS) * starsize) == 0;
   if (!same_star && !sweeptt_set_star(c, fs, starsize)) return 0;
   if (!sweeptt_set_sources(c, starts, numstart)) return 0;
-  if (!sweeptt_run(c, st)) return 0;
-  float ms = 0;
+  ConstLease lease;
+  if (!ready(c, &lease)) return 0;
+  // device -> host, overlapped with the solve of the later waves: un-pad into a ring of dense boxes on the solve
+  // stream, one contiguous copy per source on the copy stream
+  const size_t dense = (size_t)nx * ny * nz;
+  if (!ensure_out_ring(c, dense, 2 * std::max(1, std::min(numstart, 16)))) return 0;
+  size_t ring_pos = 0;
+  std::vector<char> ring_used(c->out_ring_boxes, 0);
+  const auto t_first = std::chrono::steady_clock::now();
+  auto drain = [&](int s0, int ns) -> int {
+    for (int s = s0; s < s0 + ns; ++s) {
+      const size_t slot = ring_pos++ % c->out_ring_boxes;
+      float* box = c->d_out_ring + slot * dense;
+      if (ring_used[slot]) CK(cudaStreamWaitEvent(c->stream, c->ring_copied[slot], 0));
+      CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, box, c->g, c->stream));
+      CK(cudaEventRecord(c->ring_unpadded[slot], c->stream));
+      CK(cudaStreamWaitEvent(c->copy_stream, c->ring_unpadded[slot], 0));
+      CK(cudaMemcpyAsync(tt_out[s], box, dense * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+      CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
+      ring_used[slot] = 1;
+    }
+    return 1;
+  };
+  if (!run_locked(c, st, drain)) return 0;
+  const auto t_solved = std::chrono::steady_clock::now();
+  CK(cudaStreamSynchronize(c->copy_stream));
   st->h2d_ms = h2d_ms;
   st->h2d_bytes = (long long)nx * ny * nz * 4;
-  CK(cudaEventRecord(c->ev2, c->stream));
-  // device -> host: un-pad into the dense staging box, then one contiguous copy per source
-  const size_t dense = (size_t)nx * ny * nz;
-  for (int s = 0; s < numstart; ++s) {
-    CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, c->d_stage, c->g, c->stream));
-    CK(cudaMemcpyAsync(tt_out[s], c->d_stage, dense * 4, cudaMemcpyDeviceToHost, c->stream));
-  }
-  CK(cudaEventRecord(c->ev3, c->stream));
-  CK(cudaEventSynchronize(c->ev3));
-  CK(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
-  st->d2h_ms = ms;
+  // what the copies cost on top of the solve: the tail after the last wave converged (the rest ran behind it)
+  st->d2h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_solved).count();
+  (void)t_first;
   st->d2h_bytes = (long long)dense * 4 * numstart;
   st->kernel_launches += 2 + numstart;
   return 1;
@@ -1342,6 +1545,7 @@ struct Slab {
   sweeptt_stats st{};
   int ok = 1;
   std::string err;
+  ConstLease lease;  // all slabs run the same star: they share the device's __constant__ tables
 };
 }  // namespace
 
@@ -1368,6 +1572,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   std::vector<Slab> slabs(G);
   auto cleanup = [&] {
     for (auto& sl : slabs) {
+      sl.lease.release();
       if (sl.d_flag) { cudaSetDevice(sl.device); cudaFree(sl.d_flag); }
       if (sl.ctx) sweeptt_destroy(sl.ctx);
     }
@@ -1406,6 +1611,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
       cleanup();
       return fail("slab decomposition needs the tiled kernel (star too wide for its halo)");
     }
+    if (!ready(sl.ctx, &sl.lease)) { cleanup(); return 0; }
     if (cudaMalloc(&sl.d_flag, sizeof(unsigned)) != cudaSuccess) { cleanup(); return fail("cudaMalloc failed"); }
   }
   // ---- peer access between neighbouring slabs on different devices (NVLink P2P) ------------------
