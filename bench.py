@@ -364,6 +364,32 @@ def extras_single_gpu(P, torch, W, local, stream, flush, sms, sm_max):
     return out
 
 
+def one_grid_rider(P, W, ndev):
+    """ONE source on ONE 1201x1201x251 grid: all devices of the box against one device, same code path
+    (sweeptt_solve_slabs: shared box in peer memory, halo reads fused into the relaxation kernel's TMA loads)."""
+    dims = (1201, 1201, 251)
+    v = W.heterogeneous_field(dims, 11)
+    star = P.make_star(W.star("818"))
+    start = (600, 600, 250)
+    out = {"workload": "1201x1201x251 heterogeneous (seed 11), 818-FS, 1 source at (600,600,250)", "devices": ndev}
+    sha = {}
+    for n in (1, ndev):
+        best = None
+        for _ in range(2):
+            tt, st = P.solve_slabs(v, star, start, num_slabs=n, slab_axis=0)
+            if best is None or st.solve_ms < best.solve_ms:
+                best = st
+        sha[n] = hashlib.sha256(tt.tobytes()).hexdigest()
+        out[f"solve_ms_{n}_dev"] = best.solve_ms
+        out[f"grelax_per_s_{n}_dev"] = best.relaxations / best.solve_ms / 1e6
+        out[f"devices_used_{n}"] = best.devices_used
+        del tt
+    out["speedup"] = out["solve_ms_1_dev"] / out[f"solve_ms_{ndev}_dev"]
+    out["bit_equal_to_one_device"] = sha[1] == sha[ndev]
+    out["sha256"] = sha[ndev]
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -486,6 +512,17 @@ def run_ours(args):
     P.load_library().sweeptt_release_cache()
     del hout
 
+    # ---- N>1 rider: ONE grid spread over all N devices (config 5's scheme at config 4's size), driven by rank 0 ----
+    one_grid = None
+    if world > 1 and not args.no_extras and args.workload == "config3":
+        host_group = dist.new_group(backend="gloo")     # host-side wait: no NCCL kernel spins on the devices meanwhile
+        if rank == 0:
+            try:
+                one_grid = one_grid_rider(P, W, world)
+            except Exception as e:  # a rider must never sink the headline
+                one_grid = {"failed": repr(e)}
+        dist.barrier(group=host_group)
+
     extras = None
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "config3":
         try:
@@ -548,6 +585,8 @@ def run_ours(args):
     }
     if extras is not None:
         line["extras"] = extras
+    if one_grid is not None:
+        line["one_grid_over_all_gpus"] = one_grid
     if not args.no_cpu_baseline and world == 1 and args.workload in ("config2", "config3"):
         try:
             step_s, step_v, kind, cores = cpu_reference_run(2, 1, args.workload)

@@ -198,18 +198,24 @@ size_t sweeptt_pool_bytes(sweeptt_ctx *ctx);
  * sources per launch as fit its shared-memory key snapshot, more sources run as consecutive waves. */
 long long sweeptt_tiles_per_source(sweeptt_ctx *ctx);
 
-/* ---- single huge grid: slab decomposition over the devices of one box ----- */
+/* ---- single huge grid over the devices of one box ----------------------------------------- */
 
 /* Replaces the MPI ghost-cell decomposition (mpi/16partsmpi.c:740-909,
- * mpi/sweep-tt-multistart.c:422-556; ghost width = star radius) for ONE source:
- * 1-D slabs along opts->slab_axis over devices [0,num_devices), halo planes pushed
- * to the neighbours over NVLink peer copies after every round, global convergence
- * when no slab changed.  Result is bit-identical to the single-device field. */
+ * mpi/sweep-tt-multistart.c:422-556; ghost width = star radius) for ONE source on ONE grid.
+ * opts->num_devices = number of parts (more parts than visible devices share devices round-robin);
+ * opts->slab_axis = the caller axis the grid is cut along.  The slowness box and the travel-time box
+ * are each one virtual address range whose pages are dealt block-cyclically (blocks of a few tiles
+ * along slab_axis) to the devices; every device relaxes the tiles of its own blocks, its TMA loads
+ * read halo planes straight from the owner's memory over NVLink and a changed tile wakes its
+ * neighbours through the owning device's activation keys.  There are no ghost copies and no exchange
+ * step; the host only detects quiescence (opts->rounds_per_poll rounds per look, default 4).
+ * The result is bit-identical to the single-device field.  stats->solve_ms is the host wall clock
+ * of the relaxation phase, h2d_ms / d2h_ms those of upload (incl. set-up) and gather. */
 int sweeptt_solve_slabs(const float *slowness, int nx, int ny, int nz, const struct FS *fs,
                         int starsize, struct START start, float *tt_out, const sweeptt_opts *opts,
                         sweeptt_stats *stats);
 
-/* Same, but every slab loads only its own planes (+ ghost planes) from the .vbox file with the subset
+/* Same, but every part loads only the planes of its own blocks from the .vbox file with the subset
  * reader (include/velocityboxfiler.h:741) -- what mpi/16partsmpi.c would need for models that do not
  * fit one node's memory.  Model dimensions come from the file header. */
 int sweeptt_solve_slabs_vbox(const char *vbox_path, const struct FS *fs, int starsize, struct START start,
@@ -226,8 +232,10 @@ int sweeptt_vbox_dims(const char *path, int dims[3]);
 int sweeptt_vbox_store(const char *path, const float *slowness, const int origin[3],
                        const int dims[3]);
 /* include/velocityboxfiler.h:741 vbfileloadbinarysubset via :511 vbfileopenbinary: reads the
- * sub-box with file-relative origin sub_origin (0-based index into the stored box) and size
- * sub_dims without reading the rest of the file (checksum not verified, :798-799). */
+ * sub-box of size sub_dims without reading the rest of the file (checksum not verified, :798-799).
+ * sub_origin is FILE-RELATIVE: a 0-based index into the stored box, NOT the absolute coordinates
+ * that the reference's bounds check compares with the file's min corner (:761-779, ox >= min);
+ * a caller holding absolute coordinates subtracts the origin returned by sweeptt_vbox_load. */
 int sweeptt_vbox_load_subset(const char *path, const int sub_origin[3], const int sub_dims[3],
                              float **slowness);
 /* Text dialect A "x,y,z,v" per line (include/velocityboxfiler.h:91 vbfileloadtext) and

@@ -60,7 +60,8 @@ struct SolveState {
   unsigned long long units_changed;  // ... of which lowered at least one travel time
   int max_rounds;            // 0 = unlimited; the graph WHILE loop stops here
   unsigned kmin_bits;        // smallest activation key among dirty tiles (scan pass of the compaction)
-  int pad;
+  unsigned kmin_pub;         // one grid over several devices: smallest pending key at this part's last compaction
+                             // (INF: nothing pending); read by the other parts and by the host's termination test
   // ---- single-launch (persistent) scheduling: work lists come in GENERATIONS built on the device ----
   unsigned gen;              // newest published generation; its list is work list (gen & 1)
   unsigned builder;          // generation some CTA has claimed to build (== gen + 1 while a build is running)
@@ -94,9 +95,12 @@ struct StarDev {   // star as the simple kernel / verifier read it (global memor
   int guarded;
 };
 
+constexpr int MAX_PARTS = 16;    // devices (or contexts sharing devices) that one grid can be spread over
+
 constexpr int MAX_COLUMNS = 320;
 constexpr int MAX_PATTERNS = 31;
 constexpr int MAX_COL_HD = 4096;
-constexpr int MAX_EXTRA = 256;
+constexpr int MAX_EXTRA = 128;
+constexpr int NXCLASS = 3;       // column tables per tile position along x: interior, first tile, last tile (kernels.cu c_pdesc)
 
 }  // namespace sweeptt

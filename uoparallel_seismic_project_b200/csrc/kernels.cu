@@ -48,20 +48,22 @@ namespace sweeptt {
 __constant__ ColumnDev c_cols[MAX_COLUMNS];
 __constant__ float c_col_hd[MAX_COL_HD];
 __constant__ ExtraDev c_extra[MAX_EXTRA];
-// c_pdesc[(t * MAX_PATTERNS + g) * MAX_WARPS + p]: the piece of column group g that part p runs, one 64-bit
-// constant load per group: x = first column | (end column << 16), y = index of the first column's first
-// half-distance.  Every part walks ALL groups in the same order (instruction-cache locality) and the host
+// c_pdesc[((xc * 6 + t) * MAX_PATTERNS + g) * MAX_WARPS + p]: the piece of column group g that part p runs, one
+// 32-bit constant load per group: first column | (end column << 9) | (index of the first column's first
+// half-distance << 18).  Every part walks ALL groups in the same order (instruction-cache locality) and the host
 // balances the parts' total cost.  Table t = 0: one live unit shared by all nw warps; t = 1, 2: units 0 and 1
 // of a tile with two live units; t = 3..5: the same for the single-launch kernels (their finisher warp needs a
-// longer head start).
-__constant__ uint2 c_pdesc[6 * MAX_PATTERNS * MAX_WARPS];
+// longer head start).  xc = the tile's position along x: 0 interior, 1 first tile, 2 last tile -- a unit is only 4
+// nodes wide, so at the box's x faces whole columns pull from outside the grid for every lane; those tables leave
+// them out (on the 241x241x51 box, whose 51 axis is kernel x, that is 7 % of all column evaluations).
+__constant__ unsigned c_pdesc[NXCLASS * 6 * MAX_PATTERNS * MAX_WARPS];
 
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, const uint2* pdesc, int npdesc,
+                                  const ExtraDev* extra, int nextra, const unsigned* pdesc, int npdesc,
                                   cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
   if (npdesc > 0)
-    e = cudaMemcpyToSymbolAsync(c_pdesc, pdesc, sizeof(uint2) * npdesc, 0, cudaMemcpyHostToDevice, stream);
+    e = cudaMemcpyToSymbolAsync(c_pdesc, pdesc, sizeof(unsigned) * npdesc, 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
   if (ncols > 0)
     e = cudaMemcpyToSymbolAsync(c_cols, cols, sizeof(ColumnDev) * ncols, 0, cudaMemcpyHostToDevice, stream);
@@ -320,14 +322,14 @@ __device__ __forceinline__ void relax_offsets_runtime(uint32_t kmask, const floa
 // with 16 warps per SM the other warps hide the shared-memory latency.
 template <uint32_t KMASK>
 __device__ __forceinline__ void run_pattern_range(const float* __restrict__ sv, const float* __restrict__ st, int b0,
-                                                  const uint2 d, const float (&vn)[KZ],
+                                                  const unsigned d, const float (&vn)[KZ],
                                                   const u64 (&vnE)[KZ / 2], const u64 (&vnO)[KZ / 2 - 1], u64 nz2,
                                                   float (&acc)[KZ]) {
   constexpr uint32_t GM = granules_of(KMASK);
   constexpr int NK = popc_below(KMASK, 2 * ZHALO + 1);
-  const int lo = (int)(d.x & 0xffffu), hi_ = (int)(d.x >> 16);
+  const int lo = (int)(d & 511u), hi_ = (int)((d >> 9) & 511u);
   if (lo >= hi_) return;
-  int hi = (int)d.y;
+  int hi = (int)(d >> 18);
   float W[WIN], T[WIN];
   for (int c = lo; c < hi_; ++c, hi += NK) {
     const int soff = c_cols[c].soff;
@@ -353,8 +355,8 @@ __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __res
 #pragma unroll
     for (int m = 0; m < WIN; ++m) { W[m] = 0.f; T[m] = CUDART_INF_F; }
     for (int g = 0; g < a.npat; ++g) {
-      const uint2 d = c_pdesc[g * MAX_WARPS + f0];
-      const int lo = (int)(d.x & 0xffffu), hi_ = (int)(d.x >> 16);
+      const unsigned d = c_pdesc[g * MAX_WARPS + f0];
+      const int lo = (int)(d & 511u), hi_ = (int)((d >> 9) & 511u);
       for (int c = lo; c < hi_; ++c) {
         const ColumnDev col = c_cols[c];
         const float* pv = sv + b0 + col.soff;
@@ -666,7 +668,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int nlive = (UNITS == 2 && x0 + 4 < a.g.nx) ? 2 : 1;
     const int P = NW / nlive;
     const int unit = wq / P, part = wq - unit * P;
-    const int f0 = (((PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
+    const int xc = tx == 0 ? 1 : (tx == a.g.ntx - 1 ? 2 : 0);  // tile position along x: which columns can reach the grid at all
+    const int f0 = ((xc * 6 + (PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
     const bool owner = part == 0;
     const int x = (unit << 2) | (lane >> 3);
     // smem float index of this thread's window start for the (0,0) column
@@ -855,6 +858,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       // single launch: the owners' stores (ordered before this point by the owners' barrier) must be visible
       // device-wide before any neighbour is woken up
       if constexpr (PERSIST) __threadfence();
+      else if (a.nparts > 1) __threadfence_system();  // ... system-wide before the owner of a neighbour tile on ANOTHER device is
       // a changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected;
       // the tile itself only needs another visit if its last in-tile pass still changed something
       for (int m = lane; m < NMARK; m += 32) {
@@ -865,14 +869,23 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         if (self && !last_pass_changed) reach = false;
         if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
           const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
+          unsigned* keyp = a.key;
+          const unsigned* tmaxp = a.tmax;
+          if constexpr (!PERSIST) {
+            if (a.nparts > 1) {  // the neighbour's x block may belong to another device: its owner keeps its key
+              const int o = (ux / a.tiles_per_block) % a.nparts;
+              keyp = a.part_key[o];
+              tmaxp = a.part_tmax[o];
+            }
+          }
           // Downwind filter: every candidate that one of our lowered nodes can offer is
           // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
           // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
           // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
           bool useful = true;
-          if (a.tmax != nullptr && !self)
-            useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < a.tmax[u];
-          if (useful) atomicMin(&a.key[u], tile_tmin);
+          if (tmaxp != nullptr && !self)
+            useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < __ldcg(&tmaxp[u]);
+          if (useful) atomicMin(&keyp[u], tile_tmin);
         }
       }
     }
@@ -917,7 +930,15 @@ __global__ void __launch_bounds__(256) select_tiles(const RelaxArgs a, unsigned 
   // bucket: keys within `bucket` of the smallest pending key (Dijkstra-like ordering at tile
   // granularity; travel times below the bucket are final, so their tiles are not re-relaxed with
   // inputs that are still going to change)
-  const float kmin = __uint_as_float(S->kmin_bits);
+  unsigned kmin_bits = S->kmin_bits;
+  if (a.nparts > 1) {
+    // one grid over several devices: publish our smallest pending key and follow the smallest one anywhere (a stale
+    // peer value is older, hence lower: the threshold is only ever too careful)
+    if (blockIdx.x == 0 && threadIdx.x == 0) st_volatile_u32(a.part_kmin[a.part], kmin_bits);
+    for (int q = 0; q < a.nparts; ++q)
+      if (q != a.part) kmin_bits = min(kmin_bits, ld_volatile_u32(a.part_kmin[q]));
+  }
+  const float kmin = __uint_as_float(kmin_bits);
   const unsigned thr = (a.bucket < 0.f) ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
   const unsigned k = (i < total) ? a.key[i] : 0x7f800000u;
   const bool set = (k != 0x7f800000u) && (k <= thr);
@@ -1115,67 +1136,20 @@ cudaError_t launch_min_slowness(const float* dense, long long n, unsigned* out6,
 __global__ void init_sources_kernel(const RelaxArgs a) {
   const int s = blockIdx.x;
   const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
-  if (px < 0 || px >= a.g.nx || py < 0 || py >= a.g.ny || pz < 0 || pz >= a.g.nz) return;  // start owned by another slab
-  if (threadIdx.x == 63)
+  if (px < 0 || px >= a.g.nx || py < 0 || py >= a.g.ny || pz < 0 || pz >= a.g.nz) return;
+  // (one grid over several devices: the owner of the start's x block writes the 0, every part lists its own tiles)
+  if (threadIdx.x == 63 && (a.nparts <= 1 || ((px / TX) / a.tiles_per_block) % a.nparts == a.part))
     a.tt[(size_t)s * a.g.vol + ((size_t)(px + AX) * a.g.py + (py + AY)) * a.g.pz + (pz + AZ)] = 0.0f;
   if (threadIdx.x < NMARK) {
     const int tid = threadIdx.x;
     const int ux = px / TX + tid / 9 - XREACH, uy = py / TY + (tid / 3) % 3 - 1, uz = pz / TZ + tid % 3 - 1;
-    if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
+    if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz &&
+        (a.nparts <= 1 || (ux / a.tiles_per_block) % a.nparts == a.part)) {
       const unsigned ntiles = a.g.ntx * a.g.nty * a.g.ntz;
       const unsigned pos = atomicAdd(&a.st->count[0], 1u);
       a.worklist[pos] = s * ntiles + (ux * a.g.nty + uy) * a.g.ntz + uz;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------
-// slab decomposition: min-merge the neighbour's boundary planes into our halo planes
-// (replaces the MPI ghost exchange, mpi/16partsmpi.c:760-900; min instead of overwrite keeps
-// every value a valid, monotonically decreasing upper bound)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) merge_halo_kernel(const RelaxArgs a, const float* __restrict__ peer_tt,
-                                                         BoxGeom pg, int axis, int lo, int n, int peer_lo,
-                                                         unsigned* changed_flag) {
-  // planes [lo, lo+n) of kernel axis `axis` in OUR box correspond to planes [peer_lo, peer_lo+n) in the peer's
-  const int d[3] = {a.g.nx, a.g.ny, a.g.nz};
-  int ext[3] = {d[0], d[1], d[2]};
-  ext[axis] = n;
-  const long long total = (long long)ext[0] * ext[1] * ext[2];
-  const int ntiles = a.g.ntx * a.g.nty * a.g.ntz;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c[3];
-    c[2] = (int)(i % ext[2]);
-    const long long r = i / ext[2];
-    c[1] = (int)(r % ext[1]);
-    c[0] = (int)(r / ext[1]);
-    int pc[3] = {c[0], c[1], c[2]};
-    c[axis] += lo;
-    pc[axis] += peer_lo;
-    const size_t mine = ((size_t)(c[0] + AX) * a.g.py + (c[1] + AY)) * a.g.pz + (c[2] + AZ);
-    const size_t theirs = ((size_t)(pc[0] + AX) * pg.py + (pc[1] + AY)) * pg.pz + (pc[2] + AZ);
-    const float v = peer_tt[theirs];  // peer memory over NVLink (or local when slabs share a device)
-    if (v < a.tt[mine]) {
-      a.tt[mine] = v;
-      *changed_flag = 1u;
-      const int tx = c[0] / TX, ty = c[1] / TY, tz = c[2] / TZ;
-      const unsigned bits = __float_as_uint(v);
-      for (int dx = -XREACH; dx <= XREACH; ++dx)
-        for (int dy = -1; dy <= 1; ++dy)
-          for (int dz = -1; dz <= 1; ++dz) {
-            const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-            if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz)
-              atomicMin(&a.key[((size_t)ux * a.g.nty + uy) * a.g.ntz + uz], bits);
-          }
-    }
-  }
-  (void)ntiles;
-}
-
-cudaError_t launch_merge_halo(const RelaxArgs& a, const float* peer_tt, const BoxGeom& peer_geom, int axis, int lo,
-                              int n, int peer_lo, unsigned* changed_flag, cudaStream_t stream) {
-  merge_halo_kernel<<<1184, 256, 0, stream>>>(a, peer_tt, peer_geom, axis, lo, n, peer_lo, changed_flag);
-  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1355,10 +1329,20 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
   m = __reduce_min_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(&s_min, m);
   __syncthreads();
+  if (a.nparts > 1) {  // (see select_tiles)
+    if (threadIdx.x == 0) {
+      unsigned g = s_min;
+      st_volatile_u32(a.part_kmin[a.part], g);
+      for (int q = 0; q < a.nparts; ++q)
+        if (q != a.part) g = min(g, ld_volatile_u32(a.part_kmin[q]));
+      s_min = g;
+    }
+    __syncthreads();
+  }
   const float kmin = __uint_as_float(s_min);
   const bool all = a.bucket < 0.f;
   const unsigned thr = all ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
-  const float scale = all ? 0.f : (float)FUSED_BINS / a.bucket;
+  const float scale = a.bin_scale;  // FUSED_BINS / bucket, divided on the host
   // pass A: histogram of the selected tiles' key bins
   for (unsigned i = threadIdx.x; i < total; i += 1024) {
     const unsigned k = s_keys[i];
@@ -1447,6 +1431,7 @@ __global__ void init_state_kernel(SolveState* S, int max_rounds) {
   SolveState z = {};
   z.max_rounds = max_rounds;
   z.kmin_bits = 0x7f800000u;
+  z.kmin_pub = 0x7f800000u;
   *S = z;
 }
 cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t stream) {
@@ -1456,6 +1441,22 @@ cudaError_t launch_reset_state_only(SolveState* st, int max_rounds, cudaStream_t
 cudaError_t launch_fill_tmax(const RelaxArgs& a, cudaStream_t stream) {
   const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
   fill_u32_kernel<<<(unsigned)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(a.tmax, (long long)total, 0x7f800000u);
+  return cudaGetLastError();
+}
+cudaError_t launch_reset_part(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {
+  init_state_kernel<<<1, 1, 0, stream>>>(a.st, max_rounds);
+  const size_t total = (size_t)a.nsrc * a.g.ntx * a.g.nty * a.g.ntz;
+  fill_u32_kernel<<<(unsigned)std::min<size_t>(1184, (total + 255) / 256), 256, 0, stream>>>(a.key, (long long)total, 0x7f800000u);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (a.tmax != nullptr) {
+    e = launch_fill_tmax(a, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+cudaError_t launch_init_sources(const RelaxArgs& a, cudaStream_t stream) {
+  init_sources_kernel<<<a.nsrc, 64, 0, stream>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_reset(const RelaxArgs& a, int max_rounds, cudaStream_t stream) {

@@ -27,7 +27,7 @@ int tiled_stock_star_for(const uint32_t* masks_ascending, int n, int rxy_needed)
 
 // Upload the column tables into __constant__ memory (stream ordered).
 cudaError_t upload_star_constants(const ColumnDev* cols, int ncols, const float* col_hd, int nhd,
-                                  const ExtraDev* extra, int nextra, const uint2* pdesc, int npdesc,
+                                  const ExtraDev* extra, int nextra, const unsigned* pdesc, int npdesc,
                                   cudaStream_t stream);
 
 struct RelaxArgs {
@@ -55,6 +55,16 @@ struct RelaxArgs {
   float neg_zero;              // -0.0f passed at run time (see mul2_exact in kernels.cu)
   unsigned lookahead;          // single launch: the list entry this far before the end triggers the next build
   unsigned trig_q8;            // ... but not before this fraction (in 1/256) of the list is handed out
+  // ---- one grid spread over several devices (shared_grid.cu): the boxes are ONE virtual address range whose pages
+  // live block-cyclically on the devices; every part relaxes the tiles of the x blocks it owns, reads halos from
+  // peer memory with the same TMA loads and wakes the owner of a neighbour tile through that part's key array ----
+  int nparts;                  // 0 or 1: a single context
+  int part;                    // index of this context
+  int tiles_per_block;         // x tiles per ownership block: owner(tx) = (tx / tiles_per_block) % nparts
+  unsigned* part_key[MAX_PARTS];    // every part's activation keys (peer memory)
+  unsigned* part_tmax[MAX_PARTS];   // every part's per-tile upper bounds (peer memory; nullptr = no filter)
+  unsigned* part_kmin[MAX_PARTS];   // every part's published smallest pending key: the activation bucket follows
+                                    // the smallest key on ANY device, so no device runs ahead of the front
   int npat;                    // pattern groups (generic kernel; the stock kernels know theirs at compile time)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };
@@ -79,10 +89,10 @@ cudaError_t launch_relax_simple(const RelaxArgs& a, const StarDev* star, int nst
                                 unsigned long long pulls_per_round, cudaStream_t stream);
 cudaError_t launch_advance_simple(SolveState* st, unsigned long long cond, cudaStream_t stream);
 
-// Slab decomposition: tt[planes lo..lo+n of kernel axis] = min(own, peer's planes peer_lo..); marks
-// the tiles around every lowered node; *changed_flag |= 1 when anything was lowered.
-cudaError_t launch_merge_halo(const RelaxArgs& a, const float* peer_tt, const BoxGeom& peer_geom, int axis, int lo,
-                              int n, int peer_lo, unsigned* changed_flag, cudaStream_t stream);
+// One grid over several devices: the tiles of this part around the start point go on its first work list (reset of
+// the shared box itself is done per owned block by the host: launch_fill on plane ranges).
+cudaError_t launch_reset_part(const RelaxArgs& a, int max_rounds, cudaStream_t stream);
+cudaError_t launch_init_sources(const RelaxArgs& a, cudaStream_t stream);
 
 // Fixed-point verifier.
 cudaError_t launch_count_violations(const RelaxArgs& a, int source, const StarDev* star, int nstar,

@@ -98,7 +98,7 @@ long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1
 
 void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
                    int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
-                   std::vector<double>* loads_out, double column_overhead) {
+                   std::vector<double>* loads_out, double column_overhead, const GroupRange* unit_range) {
   const int ngroups = (int)gbeg.size() - 1;
   const int feeder = nw / 2 - 1, finisher = nw - 1;  // warp indices (kernels.cu)
   auto cost = [&](int col) { return (double)__builtin_popcount(kmasks[col]) + column_overhead; };
@@ -115,9 +115,11 @@ void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& 
       if (w == feeder) load[pt] += b_feed;
       if (w == finisher) load[pt] += b_fin;
     }
+    const GroupRange* ur = unit_range ? &unit_range[table % 3 == 2 ? 1 : 0] : nullptr;
     for (int g = 0; g < ngroups && g < max_groups; ++g) {
+      const int gfirst = ur ? ur->first[g] : gbeg[g], gend = ur ? ur->end[g] : gbeg[g + 1];
       double gcost = 0;
-      for (int col = gbeg[g]; col < gbeg[g + 1]; ++col) gcost += cost(col);
+      for (int col = gfirst; col < gend; ++col) gcost += cost(col);
       double total = gcost;
       for (double l : load) total += l;
       // water-filling level: parts already above it get nothing from this group
@@ -134,7 +136,7 @@ void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& 
       // columns per part: its deficit below the level in units of the group's mean column cost, rounded by
       // largest remainder so that the counts add up (what rounding costs a part here it gets back from
       // the next groups, because the level is recomputed from the actual loads)
-      const int n = gbeg[g + 1] - gbeg[g];
+      const int n = gend - gfirst;
       const double wavg = gcost / std::max(1, n);
       std::vector<int> cntp(parts, 0);
       std::vector<std::pair<double, int>> frac;
@@ -151,12 +153,12 @@ void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& 
       for (int i = 0; given < n; i = (i + 1) % parts) { cntp[frac[i].second] += 1; ++given; }
       for (int i = parts - 1; given > n; i = (i + parts - 1) % parts)
         if (cntp[frac[i].second] > 0) { cntp[frac[i].second] -= 1; --given; }
-      int col = gbeg[g];
+      int col = gfirst;
       for (int pt = 0; pt < parts; ++pt) {
         row[pt] = (unsigned short)col;
         for (int k = 0; k < cntp[pt]; ++k, ++col) load[pt] += cost(col);
       }
-      for (int pt = parts; pt <= max_warps; ++pt) row[pt] = (unsigned short)gbeg[g + 1];
+      for (int pt = parts; pt <= max_warps; ++pt) row[pt] = (unsigned short)gend;
     }
     if (loads_out)
       for (int pt = 0; pt < parts; ++pt) (*loads_out)[(size_t)table * max_warps + pt] = load[pt];

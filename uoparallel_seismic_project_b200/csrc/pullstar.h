@@ -59,8 +59,12 @@ long long count_pulls(const PullStar& ps, int nx, int ny, int nz, int x0, int x1
 // also issues two device-wide fences per tile (measured on config 2: 6/2/50 -> 12.9 ms, 10/2/60 -> 12.7 ms)
 constexpr double kDefaultBias[2][3] = {{8.0, 2.0, 14.0}, {10.0, 2.0, 60.0}};
 
+// `unit_range` (optional): for unit 0 and unit 1 of the tile, per column group the sub-range [first, end) of columns
+// that can reach a node inside the grid at all (tiles at the x boundary of the box: the other columns pull from
+// outside the grid for every lane of the unit and are left out); tables 0, 1, 3, 4 follow unit 0, tables 2, 5 unit 1.
+struct GroupRange { std::vector<int> first, end; };
 void split_columns(const std::vector<uint32_t>& kmasks, const std::vector<int>& gbeg, int nw, int max_groups,
                    int max_warps, const double bias[2][3], std::vector<unsigned short>* psplit,
-                   std::vector<double>* loads, double column_overhead = 1.5);
+                   std::vector<double>* loads, double column_overhead = 1.5, const GroupRange* unit_range = nullptr);
 
 }  // namespace sweeptt

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cmath>
@@ -172,7 +173,8 @@ struct sweeptt_ctx {
   std::vector<ColumnDev> img_cols;
   std::vector<float> img_hd;
   std::vector<ExtraDev> img_extra;
-  std::vector<uint2> img_pdesc;
+  std::vector<unsigned> img_pdesc;
+  int consts_nx = -1;   // ... and the grid's x extent (the column tables of the first / last tile along x depend on it)
   uint64_t img_sig = 0;
   std::vector<int> pat_begin;  // column ranges per k-pattern (stock-star kernels)
   std::vector<unsigned short> psplit;  // per pattern group: first column of every fine part (kernels.cu c_psplit)
@@ -193,6 +195,7 @@ struct sweeptt_ctx {
     int slot = 1;                   // SolveState slot
     int lane = 0;                   // stream: 0 = the context's own, g >= 1 = aux_streams[g-1]
     bool persistent = false;
+    int grid = 0;                   // persistent launch: CTAs (0 = the whole device)
     cudaGraphExec_t graph = nullptr;
     CUtensorMap tm_tt{};
   };
@@ -213,7 +216,14 @@ struct sweeptt_ctx {
   std::vector<cudaEvent_t> prof_events;
   bool allow_outside_sources = false;  // slab contexts: the start may lie in another slab
   int max_inner = 1;                   // in-tile passes per tile visit
-  int force_window_axis = -1;          // slab contexts: all slabs must share one axis order
+  int force_window_axis = -1;          // forced caller axis of the kernel's register-window (z) axis
+  int force_x_axis = -1;               // one grid over several devices: caller axis that becomes kernel x (block axis)
+  bool external_boxes = false;         // d_slow / d_tt belong to a SharedBox (one grid over several devices)
+  // one grid over several devices (see RelaxArgs): this context's part of the job
+  int mp_nparts = 0, mp_part = 0, mp_tiles_per_block = 1;
+  unsigned* mp_key[MAX_PARTS] = {};
+  unsigned* mp_tmax[MAX_PARTS] = {};
+  unsigned* mp_kmin[MAX_PARTS] = {};
 };
 
 // The __constant__ star tables are per-device module state shared by every context on that device.  A compute
@@ -335,7 +345,8 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   cudaFree(c->d_out_ring);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
-  cudaFree(c->d_slow); cudaFree(c->d_tt); cudaFree(c->d_src); cudaFree(c->d_state);
+  if (!c->external_boxes) { cudaFree(c->d_slow); cudaFree(c->d_tt); }
+  cudaFree(c->d_src); cudaFree(c->d_state);
   cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_keysnap); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
   if (c->h_state) cudaFreeHost(c->h_state);
@@ -372,10 +383,8 @@ static int build_maps(sweeptt_ctx* c);
 static int encode_tt_map(sweeptt_ctx* c, float* base, int nboxes, CUtensorMap* out);
 static int choose_kernel(sweeptt_ctx* c);
 
-extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, int ny, int nz) {
-  if (!c || !slowness) return fail("sweeptt_set_model: null argument");
-  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sweeptt_set_model: bad dimensions %d x %d x %d", nx, ny, nz);
-  CK(cudaSetDevice(c->device));
+// Kernel geometry of an nx x ny x nz (caller order) model: axis order, padded dims, tiles.
+static int compute_geometry(sweeptt_ctx* c, int nx, int ny, int nz, BoxGeom* out) {
   BoxGeom g{};
   {
     // Axis order of the kernel: any permutation of the caller's axes gives the same field (the star is
@@ -386,20 +395,21 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
     const int n[3] = {nx, ny, nz};
     static const int perms[6][3] = {{0, 1, 2}, {1, 0, 2}, {0, 2, 1}, {2, 0, 1}, {1, 2, 0}, {2, 1, 0}};
     const int gran[3] = {4, TY, TZ};
-    int pick = 0;
+    int pick = -1;
     double best = -1;
     int forced = -1;
     if (const char* e = getenv("SWEEPTT_WINDOW_AXIS")) forced = std::max(0, std::min(2, atoi(e)));
     if (c->force_window_axis >= 0) forced = c->force_window_axis;
+    if (c->force_x_axis >= 0 && forced == c->force_x_axis) forced = -1;  // (cannot be both)
     for (int pi = 0; pi < 6; ++pi) {
       if (forced >= 0 && perms[pi][2] != forced) continue;
-      if (c->force_window_axis >= 0 && pi != 0) continue;  // slabs: the caller's order exactly
+      if (c->force_x_axis >= 0 && perms[pi][0] != c->force_x_axis) continue;
       double eff = 1.0;
       for (int q = 0; q < 3; ++q) {
         const int len = n[perms[pi][q]];
         eff *= (double)len / (double)(((len + gran[q] - 1) / gran[q]) * gran[q]);
       }
-      if (eff > best * 1.02) { best = eff; pick = pi; }  // a permutation must pay for its transposing copies
+      if (pick < 0 || eff > best * 1.02) { best = eff; pick = pi; }  // a permutation must pay for its transposing copies
     }
     for (int q = 0; q < 3; ++q) g.perm[q] = perms[pick][q];
     if (getenv("SWEEPTT_DEBUG"))
@@ -417,6 +427,17 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
   g.sx = (long long)g.py * g.pz;
   g.vol = (long long)g.px * g.sx;
   if ((long long)g.ntx * g.nty * g.ntz > 0x7fffffffLL) return fail("grid too large for 32-bit tile ids");
+  *out = g;
+  return 1;
+}
+
+extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, int ny, int nz) {
+  if (!c || !slowness) return fail("sweeptt_set_model: null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sweeptt_set_model: bad dimensions %d x %d x %d", nx, ny, nz);
+  CK(cudaSetDevice(c->device));
+  BoxGeom g{};
+  if (!compute_geometry(c, nx, ny, nz, &g)) return 0;
+  nx = g.nx; ny = g.ny; nz = g.nz;  // from here on: kernel axis order
   const bool same = c->have_model && c->g.px == g.px && c->g.py == g.py && c->g.pz == g.pz;
   const bool perm_changed = !c->have_model || std::memcmp(c->g.perm, g.perm, sizeof g.perm) != 0;
   if (!same) {
@@ -445,7 +466,10 @@ extern "C" int sweeptt_set_model(sweeptt_ctx* c, const float* slowness, int nx, 
     CK(cudaStreamSynchronize(c->stream));
     float vmin;
     std::memcpy(&vmin, &r[0], 4);
-    c->min_slowness = (r[1] || !std::isfinite(vmin)) ? -1.f : vmin;
+    if (r[1])
+      return fail("sweeptt_set_model: the model holds negative or NaN slowness values (travel times would not be "
+                  "bounded below; the reference itself never converges on such input)");
+    c->min_slowness = !std::isfinite(vmin) ? -1.f : vmin;
     double sum;
     unsigned long long cnt;
     std::memcpy(&sum, &r[2], 8);
@@ -588,44 +612,15 @@ static int choose_kernel(sweeptt_ctx* c) {
   const char* force = getenv("SWEEPTT_FORCE_RXY");  // testing: run a small star in a wider halo variant
   if (force && atoi(force) >= rxy) { rxy = tiled_variant_for_radius(atoi(force)); stock = 0; }
   CK(tiled_prepare(rxy, stock, c->device, &c->tl));
-  {
-    // Share the star's columns out between the compute warps (kernels.cu, c_psplit).  Column groups: the
-    // k-pattern groups for a stock-star kernel (one unrolled code block each), else plain chunks of the
-    // column list (the generic kernel reads every column's mask at run time).  Every warp walks ALL groups
-    // in the same order and runs a contiguous piece of each, so the pieces of a group are just cut points.
-    // Three tables: a tile with one live unit spreads it over all nw warps (table 0); with two live units
-    // each gets nw/2 warps (tables 1 and 2).  Some warps have other duties and get a head start (cost units,
-    // 1 unit = one k offset of one column): the unit owners finish the tile (min cells, pin, stores), the
-    // feeder warp drives the TMA ring, the finisher warp wakes the neighbours and keeps the books.
+  if (!stock) {
+    // generic kernel (it reads every column's mask at run time): the column groups are plain chunks of the list
     const int nw = c->tl.nw;
     const int ncols = (int)c->dev_columns.size();
     std::vector<int> gbeg;
-    if (stock) {
-      gbeg = c->pat_begin;
-    } else {
-      const int per = std::max(nw, (ncols + MAX_PATTERNS - 1) / MAX_PATTERNS);
-      for (int i = 0; i < ncols; i += per) gbeg.push_back(i);
-      gbeg.push_back(ncols);
-      c->pat_begin = gbeg;
-    }
-    // head starts: defaults in pullstar.h
-    double bias[2][3];
-    std::memcpy(bias, kDefaultBias, sizeof bias);
-    if (const char* e = getenv("SWEEPTT_BIAS"))
-      sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &bias[0][0], &bias[0][1], &bias[0][2], &bias[1][0], &bias[1][1], &bias[1][2]);
-    std::vector<uint32_t> kmasks(c->dev_columns.size());
-    for (size_t i = 0; i < kmasks.size(); ++i) kmasks[i] = c->dev_columns[i].kmask;
-    std::vector<double> loads;
-    double col_overhead = 1.5;  // window loads + set-up of a column, in units of one k offset
-    if (const char* e = getenv("SWEEPTT_COLCOST")) col_overhead = atof(e);
-    split_columns(kmasks, gbeg, nw, MAX_PATTERNS, MAX_WARPS, bias, &c->psplit, &loads, col_overhead);
-    if (getenv("SWEEPTT_DEBUG"))
-      for (int table = 0; table < 6; ++table) {
-        const int parts = table % 3 == 0 ? nw : nw / 2;
-        fprintf(stderr, "sweeptt: column split table %d loads:", table);
-        for (int pt = 0; pt < parts; ++pt) fprintf(stderr, " %.1f", loads[(size_t)table * MAX_WARPS + pt]);
-        fprintf(stderr, "\n");
-      }
+    const int per = std::max(nw, (ncols + MAX_PATTERNS - 1) / MAX_PATTERNS);
+    for (int i = 0; i < ncols; i += per) gbeg.push_back(i);
+    gbeg.push_back(ncols);
+    c->pat_begin = gbeg;
   }
   c->kernel_used = SWEEPTT_KERNEL_TILED;
   c->maps_valid = false;
@@ -635,9 +630,69 @@ static int choose_kernel(sweeptt_ctx* c) {
 
 // Host image of the context's __constant__ tables (rebuilt after set_star / a kernel change) and its content hash.
 static int build_const_image(sweeptt_ctx* c) {
-  if (c->consts_rxy == c->tl.rxy) return 1;
+  if (c->consts_rxy == c->tl.rxy && c->consts_nx == c->g.nx) return 1;
   int sxd, syd, szd;
   tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
+  {
+    // Share the star's columns out between the compute warps (kernels.cu, c_pdesc).  Column groups: the
+    // k-pattern groups for a stock-star kernel (one unrolled code block each), else plain chunks of the
+    // column list.  Every warp walks ALL groups in the same order and runs a contiguous piece of each, so
+    // the pieces of a group are just cut points.  Per tile position along x (interior / first / last tile):
+    // three layouts -- a tile with one live unit spreads it over all nw warps (table 0); with two live units
+    // each gets nw/2 warps (tables 1 and 2) -- times two sets of head starts (round-based / single-launch
+    // kernels; cost units, 1 unit = one k offset of one column): the unit owners finish the tile (min cells,
+    // pin, stores), the feeder warp drives the TMA ring, the finisher warp wakes the neighbours and keeps the
+    // books.  At the first and last tile along x only the columns that can reach a node INSIDE the grid from
+    // some in-grid lane of the unit are shared out (columns are sorted by i within a group, so they stay a
+    // contiguous sub-range); the others would only evaluate pulls across the box boundary.
+    const int nw = c->tl.nw;
+    const std::vector<int>& gbeg = c->pat_begin;
+    const int ngroups = (int)gbeg.size() - 1;
+    double bias[2][3];
+    std::memcpy(bias, kDefaultBias, sizeof bias);
+    if (const char* e = getenv("SWEEPTT_BIAS"))
+      sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &bias[0][0], &bias[0][1], &bias[0][2], &bias[1][0], &bias[1][1], &bias[1][2]);
+    std::vector<uint32_t> kmasks(c->dev_columns.size());
+    for (size_t i = 0; i < kmasks.size(); ++i) kmasks[i] = c->dev_columns[i].kmask;
+    double col_overhead = 1.5;  // window loads + set-up of a column, in units of one k offset
+    if (const char* e = getenv("SWEEPTT_COLCOST")) col_overhead = atof(e);
+    const bool clip = !getenv("SWEEPTT_NO_XCLIP");
+    c->psplit.assign((size_t)NXCLASS * 6 * MAX_PATTERNS * (MAX_WARPS + 1), 0);
+    for (int xc = 0; xc < NXCLASS; ++xc) {
+      GroupRange ur[2];
+      const int tx = xc == 0 ? -1 : xc == 1 ? 0 : c->g.ntx - 1;
+      for (int u = 0; u < 2; ++u) {
+        // i range of unit u's columns that connect an in-grid lane with an in-grid node
+        int imin = -RXY_MAX - 1, imax = RXY_MAX + 1;
+        if (clip && tx >= 0) {
+          const int xlo = tx * TX + 4 * u, xhi = std::min(xlo + 3, c->g.nx - 1);
+          if (xlo <= xhi) { imin = -xhi; imax = c->g.nx - 1 - xlo; }
+        }
+        ur[u].first.resize(ngroups); ur[u].end.resize(ngroups);
+        for (int g = 0; g < ngroups; ++g) {
+          int f = gbeg[g], e = gbeg[g + 1];
+          bool sorted = true;  // (columns of a group come in (i,j) order; anything else keeps the whole group)
+          for (int col = gbeg[g] + 1; col < gbeg[g + 1]; ++col) sorted = sorted && c->dev_columns[col - 1].i <= c->dev_columns[col].i;
+          if (sorted) {
+            while (f < e && c->dev_columns[f].i < imin) ++f;
+            while (e > f && c->dev_columns[e - 1].i > imax) --e;
+          }
+          ur[u].first[g] = f; ur[u].end[g] = e;
+        }
+      }
+      std::vector<unsigned short> ps;
+      std::vector<double> loads;
+      split_columns(kmasks, gbeg, nw, MAX_PATTERNS, MAX_WARPS, bias, &ps, &loads, col_overhead, ur);
+      std::copy(ps.begin(), ps.end(), c->psplit.begin() + (size_t)xc * 6 * MAX_PATTERNS * (MAX_WARPS + 1));
+      if (getenv("SWEEPTT_DEBUG"))
+        for (int table = 0; table < 6; ++table) {
+          const int parts = table % 3 == 0 ? nw : nw / 2;
+          fprintf(stderr, "sweeptt: column split x-class %d table %d loads:", xc, table);
+          for (int pt = 0; pt < parts; ++pt) fprintf(stderr, " %.1f", loads[(size_t)table * MAX_WARPS + pt]);
+          fprintf(stderr, "\n");
+        }
+    }
+  }
   // columns in upload order (pattern-sorted, even-padded); half-distances re-packed in the same
   // order so that a pattern group's hd values are contiguous; two spare entries at the end
   std::vector<ColumnDev>& cols = c->img_cols;
@@ -669,15 +724,15 @@ static int build_const_image(sweeptt_ctx* c) {
     ex[i] = ExtraDev{p.i, p.j, p.k, p.i * syd * szd + p.j * szd + p.k, p.hd, p.guarded, 0, 0};
   }
   // per (table, group, part): the part's piece of the group + where its half-distances start (kernels.cu c_pdesc)
-  std::vector<uint2>& pdesc = c->img_pdesc;
-  pdesc.assign((size_t)6 * MAX_PATTERNS * MAX_WARPS, make_uint2(0u, 0u));
-  for (int table = 0; table < 6; ++table)
+  std::vector<unsigned>& pdesc = c->img_pdesc;
+  pdesc.assign((size_t)NXCLASS * 6 * MAX_PATTERNS * MAX_WARPS, 0u);
+  for (int table = 0; table < NXCLASS * 6; ++table)
     for (int g = 0; g + 1 < (int)c->pat_begin.size() && g < MAX_PATTERNS; ++g)
       for (int pt = 0; pt < MAX_WARPS; ++pt) {
         const unsigned short* row = &c->psplit[((size_t)table * MAX_PATTERNS + g) * (MAX_WARPS + 1)];
         const unsigned lo = row[pt], hi = row[pt + 1];
         pdesc[((size_t)table * MAX_PATTERNS + g) * MAX_WARPS + pt] =
-            make_uint2(lo | (hi << 16), lo < hi ? (unsigned)cols[lo].hd_begin : 0u);
+            lo | (hi << 9) | ((lo < hi ? (unsigned)cols[lo].hd_begin : 0u) << 18);
       }
   uint64_t sig = 1469598103934665603ull;
   auto mix = [&sig](const void* p, size_t n) {
@@ -687,9 +742,10 @@ static int build_const_image(sweeptt_ctx* c) {
   mix(cols.data(), cols.size() * sizeof(ColumnDev));
   mix(hd_packed.data(), hd_packed.size() * sizeof(float));
   mix(ex.data(), ex.size() * sizeof(ExtraDev));
-  mix(pdesc.data(), pdesc.size() * sizeof(uint2));
+  mix(pdesc.data(), pdesc.size() * sizeof(unsigned));
   c->img_sig = sig | 1ull;
   c->consts_rxy = c->tl.rxy;
+  c->consts_nx = c->g.nx;
   return 1;
 }
 
@@ -844,6 +900,12 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.nextra = (int)c->star.extra.size();
   a.neg_zero = -0.0f;
   a.max_inner = c->max_inner;
+  a.nparts = c->mp_nparts; a.part = c->mp_part; a.tiles_per_block = std::max(1, c->mp_tiles_per_block);
+  for (int q = 0; q < MAX_PARTS; ++q) {
+    a.part_key[q] = c->mp_key[q];
+    a.part_tmax[q] = a.tmax ? c->mp_tmax[q] : nullptr;
+    a.part_kmin[q] = c->mp_kmin[q];
+  }
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   a.npat = (int)c->pat_begin.size() - 1;
   {
@@ -1010,23 +1072,30 @@ static int build_plan(sweeptt_ctx* c) {
   int want_groups = 2;
   if (const char* env = getenv("SWEEPTT_GROUPS")) want_groups = atoi(env);
   want_groups = std::max(1, std::min(want_groups, MAX_GROUPS));
+  // Persistent waves may run K at a time, each on 1/K of the SMs (its own stream): a wave's start and end expose
+  // fewer ready tiles than there are SMs (the front is small), and the time lost there shrinks with the SMs per wave.
+  int kstreams = 1;
+  if (const char* e = getenv("SWEEPTT_WAVE_STREAMS")) kstreams = std::max(1, std::min(atoi(e), MAX_GROUPS));
+  const int nwaves_total = (c->nsrc + wave_size - 1) / wave_size;
+  if (!persistent || nwaves_total < 2 * kstreams) kstreams = 1;
   int slot = 1, wave = 0;
   for (int s0 = 0; s0 < c->nsrc; s0 += wave_size, ++wave) {
     const int ns = std::min(wave_size, c->nsrc - s0);
     const int parts = persistent ? 1 : std::min(want_groups, ns);
     for (int g = 0; g < parts; ++g) {
       sweeptt_ctx::Slice sl;
-      sl.wave = wave;
+      sl.wave = persistent ? wave / kstreams : wave;  // (slices of one "wave" are enqueued together)
       sl.s0 = s0 + (int)((long long)ns * g / parts);
       sl.ns = s0 + (int)((long long)ns * (g + 1) / parts) - sl.s0;
       sl.slot = slot++;
-      sl.lane = g;
+      sl.lane = persistent ? wave % kstreams : g;
+      sl.grid = (persistent && kstreams > 1) ? std::max(1, c->tl.grid_persistent / kstreams) : 0;
       sl.persistent = persistent;
       if (slot > STATE_SLOTS) return fail("too many slices in the solve plan (%d sources in waves of %d)", c->nsrc, wave_size);
       c->plan.push_back(sl);
     }
   }
-  c->plan_waves = wave;
+  c->plan_waves = persistent ? (wave + kstreams - 1) / kstreams : wave;
   int lanes = 1;
   for (const auto& sl : c->plan) lanes = std::max(lanes, sl.lane + 1);
   while ((int)c->aux_streams.size() < lanes - 1) {
@@ -1075,8 +1144,11 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
   if (loop == SWEEPTT_LOOP_AUTO) loop = SWEEPTT_LOOP_GRAPH;
   const bool profile = c->opts.profile_kernels != 0;
   if (profile || !to_convergence) loop = SWEEPTT_LOOP_BATCHED;
-  if (!read_state(c)) return 0;
-  const int rounds_before = c->h_state->round;
+  int rounds_before = 0;
+  if (stats || to_convergence) {  // (a fixed batch without statistics needs no look at the state first)
+    if (!read_state(c)) return 0;
+    rounds_before = c->h_state->round;
+  }
   long long launches = 0, relax_launches = 0;
   double relax_ms = 0;
 
@@ -1143,49 +1215,78 @@ static int run_rounds(sweeptt_ctx* c, bool to_convergence, int fixed_rounds, int
 // Runs the solve plan: every wave is enqueued without waiting for the one before it; `after_wave(s0, ns)` (may be
 // empty) is called as soon as a wave's work is on the context's stream -- whatever it enqueues there runs when the
 // wave's sources have converged (sweeptt_solve un-pads them and sends them to the host while the next wave runs).
-static int run_plan(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int)>& after_wave) {
+static int run_plan(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int, cudaStream_t)>& after_wave) {
   if (!build_plan(c)) return 0;
   const bool profile = c->opts.profile_kernels != 0;  // (persistent waves only: run_plan is not used otherwise)
   size_t ev_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  std::vector<char> lane_used(1 + c->aux_streams.size(), 0);
+  auto lane_stream = [&](int lane) -> cudaStream_t {
+    cudaStream_t st = lane ? c->aux_streams[lane - 1] : c->stream;
+    if (lane && !lane_used[lane]) cudaStreamWaitEvent(st, c->ev_fork, 0);
+    lane_used[lane] = 1;
+    return st;
+  };
   size_t i = 0;
   while (i < c->plan.size()) {
+    if (c->plan[i].persistent) {
+      // a wave = one single-launch solve; waves on different lanes (streams) never wait for each other
+      const auto& sl = c->plan[i];
+      cudaStream_t st = lane_stream(sl.lane);
+      RelaxArgs a = slice_args(c, sl);
+      TiledLaunch tl = c->tl;
+      if (sl.grid > 0) {
+        a.lookahead = (unsigned)((unsigned long long)a.lookahead * sl.grid / std::max(1, tl.grid_persistent));
+        tl.grid_persistent = sl.grid;
+      }
+      CK(launch_reset(a, c->opts.max_rounds, st));
+      CK(launch_persist_begin(a, st));
+      if (profile) {
+        while (c->prof_events.size() < ev_used + 2) {
+          cudaEvent_t e;
+          CK(cudaEventCreate(&e));
+          c->prof_events.push_back(e);
+        }
+        CK(cudaEventRecord(c->prof_events[ev_used], st));
+      }
+      CK(launch_relax_persistent(tl, c->tm_slow, sl.tm_tt, a, st));
+      if (profile) { CK(cudaEventRecord(c->prof_events[ev_used + 1], st)); ev_used += 2; }
+      CK(launch_persist_check(a, st));  // any key still pending after "done" -> kmin_bits != INF (read below)
+      if (after_wave && !after_wave(sl.s0, sl.ns, st)) return 0;
+      ++i;
+      continue;
+    }
+    // a wave of source groups: G WHILE graphs side by side, joined on the context's stream
     const int wave = c->plan[i].wave;
     size_t j = i;
     while (j < c->plan.size() && c->plan[j].wave == wave) ++j;
-    if (j - i > 1) CK(cudaEventRecord(c->ev_fork, c->stream));
+    if (i > 0) {  // (lanes start after whatever the context's stream did before)
+      CK(cudaEventRecord(c->ev_fork, c->stream));
+      for (size_t k = i; k < j; ++k)
+        if (c->plan[k].lane) CK(cudaStreamWaitEvent(c->aux_streams[c->plan[k].lane - 1], c->ev_fork, 0));
+    }
     for (size_t k = i; k < j; ++k) {
       const auto& sl = c->plan[k];
-      cudaStream_t st = sl.lane ? c->aux_streams[sl.lane - 1] : c->stream;
-      if (sl.lane) CK(cudaStreamWaitEvent(st, c->ev_fork, 0));
-      const RelaxArgs a = slice_args(c, sl);
-      CK(launch_reset(a, c->opts.max_rounds, st));
-      if (sl.persistent) {
-        CK(launch_persist_begin(a, st));
-        if (profile) {
-          while (c->prof_events.size() < ev_used + 2) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            c->prof_events.push_back(e);
-          }
-          CK(cudaEventRecord(c->prof_events[ev_used], st));
-        }
-        CK(launch_relax_persistent(c->tl, c->tm_slow, sl.tm_tt, a, st));
-        if (profile) { CK(cudaEventRecord(c->prof_events[ev_used + 1], st)); ev_used += 2; }
-        CK(launch_persist_check(a, st));  // any key still pending after "done" -> kmin_bits != INF (read below)
-      } else {
-        CK(cudaGraphLaunch(sl.graph, st));
-      }
+      cudaStream_t st = lane_stream(sl.lane);
+      CK(launch_reset(slice_args(c, sl), c->opts.max_rounds, st));
+      CK(cudaGraphLaunch(sl.graph, st));
       if (sl.lane) CK(cudaEventRecord(c->aux_done[sl.lane - 1], st));
     }
     for (size_t k = i; k < j; ++k)
       if (c->plan[k].lane) CK(cudaStreamWaitEvent(c->stream, c->aux_done[c->plan[k].lane - 1], 0));
     if (after_wave) {
       const int s0 = c->plan[i].s0, s1 = c->plan[j - 1].s0 + c->plan[j - 1].ns;
-      if (!after_wave(s0, s1 - s0)) return 0;
+      if (!after_wave(s0, s1 - s0, c->stream)) return 0;
     }
     i = j;
   }
+  // join the lanes of independent persistent waves
+  for (size_t lane = 1; lane < lane_used.size(); ++lane)
+    if (lane_used[lane] && !c->plan.empty() && c->plan[0].persistent) {
+      CK(cudaEventRecord(c->aux_done[lane - 1], c->aux_streams[lane - 1]));
+      CK(cudaStreamWaitEvent(c->stream, c->aux_done[lane - 1], 0));
+    }
   CK(cudaEventRecord(c->ev1, c->stream));
   const size_t nslots = 1 + c->plan.size();
   CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState) * nslots, cudaMemcpyDeviceToHost, c->stream));
@@ -1250,7 +1351,7 @@ static bool plan_usable(sweeptt_ctx* c) {
   return true;
 }
 
-static int run_locked(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int)>& after_wave) {
+static int run_locked(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<int(int, int, cudaStream_t)>& after_wave) {
   if (stats) { std::memset(stats, 0, sizeof *stats); }
   if (plan_usable(c)) return run_plan(c, stats, after_wave);
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -1263,7 +1364,7 @@ static int run_locked(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   if (stats) { stats->solve_ms = ms; stats->kernel_launches += 4; }
   if (changed && c->opts.max_rounds > 0) return fail("not converged after max_rounds = %d rounds", c->opts.max_rounds);
-  if (after_wave && !after_wave(0, c->nsrc)) return 0;
+  if (after_wave && !after_wave(0, c->nsrc, c->stream)) return 0;
   return 1;
 }
 
@@ -1443,13 +1544,13 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
   size_t ring_pos = 0;
   std::vector<char> ring_used(c->out_ring_boxes, 0);
   const auto t_first = std::chrono::steady_clock::now();
-  auto drain = [&](int s0, int ns) -> int {
+  auto drain = [&](int s0, int ns, cudaStream_t st) -> int {
     for (int s = s0; s < s0 + ns; ++s) {
       const size_t slot = ring_pos++ % c->out_ring_boxes;
       float* box = c->d_out_ring + slot * dense;
-      if (ring_used[slot]) CK(cudaStreamWaitEvent(c->stream, c->ring_copied[slot], 0));
-      CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, box, c->g, c->stream));
-      CK(cudaEventRecord(c->ring_unpadded[slot], c->stream));
+      if (ring_used[slot]) CK(cudaStreamWaitEvent(st, c->ring_copied[slot], 0));
+      CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, box, c->g, st));
+      CK(cudaEventRecord(c->ring_unpadded[slot], st));
       CK(cudaStreamWaitEvent(c->copy_stream, c->ring_unpadded[slot], 0));
       CK(cudaMemcpyAsync(tt_out[s], box, dense * 4, cudaMemcpyDeviceToHost, c->copy_stream));
       CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
@@ -1533,19 +1634,163 @@ extern "C" int sweeptt_solve(const float* slowness, int nx, int ny, int nz, cons
 }
 
 // ---------------------------------------------------------------------------------------
-// single huge grid: 1-D slab decomposition over the devices of one box
+// single huge grid over the devices of one box: ONE shared box in peer memory
 // ---------------------------------------------------------------------------------------
+// Replaces the MPI ghost-cell decomposition (mpi/16partsmpi.c:740-909: 16 ranks, ghost width 7, Isend/Irecv of the
+// ghost planes every sweep, Allreduce of the change flag).  B200-native form: the slowness box and the travel-time
+// box are each ONE virtual address range (CUDA virtual memory management) whose physical pages live BLOCK-CYCLICALLY
+// on the devices -- blocks of a few tiles along the kernel's x axis, dealt round-robin, so that a single expanding
+// front keeps every device busy.  Every device ("part") relaxes the tiles of the blocks it owns with the unchanged
+// tiled kernel: its TMA loads fetch halo planes that belong to a neighbour block straight from the owner's memory
+// over NVLink, its stores go to its own pages, and a changed tile wakes a neighbour tile by an atomicMin on the key
+// array of THAT tile's owner.  There is no halo exchange step, no ghost copy and no per-sweep host synchronisation of
+// the data path: the transfer is fused into the relaxation kernel tile by tile.  All values only ever decrease and
+// every read is a valid upper bound, so stale remote reads cost work, never correctness, and the fixed point is the
+// single-device field bit for bit.  The devices follow ONE activation front (each publishes its smallest pending key,
+// the bucket threshold hangs on the smallest one anywhere); termination is detected by the host threads without any
+// barrier: all parts idle over a window in which every part ran a complete batch that found nothing.
 namespace {
-struct Slab {
+
+struct VmmApi {
+  PFN_cuMemGetAllocationGranularity_v10020 granularity = nullptr;
+  PFN_cuMemAddressReserve_v10020 reserve = nullptr;
+  PFN_cuMemCreate_v10020 create = nullptr;
+  PFN_cuMemMap_v10020 map = nullptr;
+  PFN_cuMemSetAccess_v10020 set_access = nullptr;
+  PFN_cuMemUnmap_v10020 unmap = nullptr;
+  PFN_cuMemRelease_v10020 release = nullptr;
+  PFN_cuMemAddressFree_v10020 address_free = nullptr;
+  bool ok = false;
+};
+const VmmApi& vmm() {
+  static VmmApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char* name) -> void* {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+      return p;
+    };
+    api.granularity = (PFN_cuMemGetAllocationGranularity_v10020)get("cuMemGetAllocationGranularity");
+    api.reserve = (PFN_cuMemAddressReserve_v10020)get("cuMemAddressReserve");
+    api.create = (PFN_cuMemCreate_v10020)get("cuMemCreate");
+    api.map = (PFN_cuMemMap_v10020)get("cuMemMap");
+    api.set_access = (PFN_cuMemSetAccess_v10020)get("cuMemSetAccess");
+    api.unmap = (PFN_cuMemUnmap_v10020)get("cuMemUnmap");
+    api.release = (PFN_cuMemRelease_v10020)get("cuMemRelease");
+    api.address_free = (PFN_cuMemAddressFree_v10020)get("cuMemAddressFree");
+    api.ok = api.granularity && api.reserve && api.create && api.map && api.set_access && api.unmap && api.release &&
+             api.address_free;
+  });
+  return api;
+}
+
+// One virtual address range, chunk c backed by memory of device chunk_dev[c]; readable and writable by `devices`.
+struct SharedBox {
+  CUdeviceptr va = 0;
+  size_t bytes = 0;
+  struct Chunk { size_t off = 0, size = 0; int device = 0; bool mapped = false; };
+  std::vector<Chunk> chunks;
+
+  int create(const std::vector<size_t>& cuts, const std::vector<int>& chunk_dev, const std::vector<int>& devices) {
+    const VmmApi& v = vmm();
+    if (!v.ok) return fail("CUDA virtual memory management entry points are not available from this driver");
+    bytes = cuts.back();
+    CUresult r = v.reserve(&va, bytes, 0, 0, 0);
+    if (r != CUDA_SUCCESS) { va = 0; return fail("cuMemAddressReserve(%zu bytes) failed: %d", bytes, (int)r); }
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+      Chunk ch;
+      ch.off = cuts[c]; ch.size = cuts[c + 1] - cuts[c]; ch.device = chunk_dev[c];
+      if (ch.size == 0) continue;
+      CUmemAllocationProp prop = {};
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = ch.device;
+      CUmemGenericAllocationHandle h;
+      r = v.create(&h, ch.size, &prop, 0);
+      if (r != CUDA_SUCCESS) return fail("cuMemCreate(%zu bytes on device %d) failed: %d", ch.size, ch.device, (int)r);
+      r = v.map(va + ch.off, ch.size, 0, h, 0);
+      v.release(h);  // the mapping keeps the memory alive
+      if (r != CUDA_SUCCESS) return fail("cuMemMap failed: %d", (int)r);
+      ch.mapped = true;
+      chunks.push_back(ch);
+    }
+    std::vector<CUmemAccessDesc> acc;
+    for (int d : devices) {
+      CUmemAccessDesc a = {};
+      a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      a.location.id = d;
+      a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      acc.push_back(a);
+    }
+    r = v.set_access(va, bytes, acc.data(), acc.size());
+    if (r != CUDA_SUCCESS) return fail("cuMemSetAccess failed: %d (peer access between the devices is required)", (int)r);
+    return 1;
+  }
+  void destroy() {
+    const VmmApi& v = vmm();
+    for (auto& ch : chunks)
+      if (ch.mapped) v.unmap(va + ch.off, ch.size);
+    chunks.clear();
+    if (va) v.address_free(va, bytes);
+    va = 0; bytes = 0;
+  }
+};
+
+struct Part {
   sweeptt_ctx* ctx = nullptr;
   int device = 0;
-  int lo = 0, hi = 0;    // owned planes [lo,hi) of the slab axis (caller coordinates)
-  int blo = 0, bhi = 0;  // planes held = owned + halo
-  unsigned* d_flag = nullptr;
-  sweeptt_stats st{};
+  std::vector<std::pair<int, int>> blocks;  // owned planes [x0,x1) of the kernel's x axis (logical coordinates)
+  ConstLease lease;
   int ok = 1;
   std::string err;
-  ConstLease lease;  // all slabs run the same star: they share the device's __constant__ tables
+  double min_slow = std::numeric_limits<double>::infinity(), sum_slow = 0;
+  unsigned long long cnt_slow = 0;
+  bool bad_slow = false;
+};
+
+// Termination of the asynchronous multi-device relaxation (no barrier): every part publishes after each batch how many
+// tiles it has relaxed in total and whether anything is pending; the job is finished when all parts are idle over a
+// window in which every part completed at least two further batches (so at least one started after the window opened
+// and saw every wake-up sent before it) without relaxing a single tile.
+struct Quiescence {
+  std::mutex mu;
+  int n = 0;
+  std::vector<long long> seq, visits, seq0, visits0;
+  std::vector<char> idle;
+  bool window = false, done = false, failed = false;
+  explicit Quiescence(int parts) : n(parts), seq(parts, 0), visits(parts, 0), seq0(parts, 0), visits0(parts, 0), idle(parts, 0) {}
+  bool report(int p, long long total_visits, bool is_idle) {  // returns true when the job is finished
+    std::lock_guard<std::mutex> lk(mu);
+    if (done || failed) return true;
+    seq[p] += 1; visits[p] = total_visits; idle[p] = is_idle;
+    bool all_idle = true;
+    for (int q = 0; q < n; ++q) all_idle = all_idle && idle[q] && seq[q] > 0;
+    if (!all_idle) { window = false; return false; }
+    if (!window) { seq0 = seq; visits0 = visits; window = true; return false; }
+    for (int q = 0; q < n; ++q) {
+      if (visits[q] != visits0[q]) { seq0 = seq; visits0 = visits; return false; }  // (cannot happen while idle; restart)
+      if (seq[q] < seq0[q] + 2) return false;
+    }
+    done = true;
+    return true;
+  }
+  void abort() { std::lock_guard<std::mutex> lk(mu); failed = true; }
+};
+
+// simple reusable barrier for the setup phases (std::barrier needs C++20)
+struct PhaseBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  int n, waiting = 0, phase = 0;
+  explicit PhaseBarrier(int parts) : n(parts) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    const int ph = phase;
+    if (++waiting == n) { waiting = 0; ++phase; cv.notify_all(); }
+    else cv.wait(lk, [&] { return phase != ph; });
+  }
 };
 }  // namespace
 
@@ -1558,159 +1803,297 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof o, opts->struct_size > 0 ? opts->struct_size : sizeof o));
   const int ndev = sweeptt_device_count();
   if (ndev <= 0) return fail("no CUDA device available: the sweep has no CPU fallback");
-  const int G = std::max(1, o.num_devices);  // slabs; more slabs than devices share devices round-robin
+  const int G = std::max(1, o.num_devices);  // parts; more parts than devices share devices round-robin
+  if (G > MAX_PARTS) return fail("at most %d parts", MAX_PARTS);
   const int axis = o.slab_axis;
   if (axis < 0 || axis > 2) return fail("slab_axis must be 0 (x), 1 (y) or 2 (z)");
   const int n[3] = {nx, ny, nz};
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("bad dimensions %d x %d x %d", nx, ny, nz);
   if (start.i < 0 || start.i >= nx || start.j < 0 || start.j >= ny || start.k < 0 || start.k >= nz)
     return fail("start point (%d,%d,%d) is outside the %d x %d x %d model", start.i, start.j, start.k, nx, ny, nz);
   if (G > n[axis]) return fail("more slabs (%d) than planes (%d) along the slab axis", G, n[axis]);
-  int R = 0;  // ghost width = star radius along the slab axis (mpi/16partsmpi.c:65 `ghostcell`)
-  for (int l = 0; l < starsize; ++l) R = std::max(R, std::abs(axis == 0 ? fs[l].i : axis == 1 ? fs[l].j : fs[l].k));
-  const size_t stride[3] = {(size_t)ny * nz, (size_t)nz, 1};
 
-  std::vector<Slab> slabs(G);
+  std::vector<Part> parts(G);
+  SharedBox box_slow, box_tt;
+  std::vector<int> devices;
+  for (int p = 0; p < G; ++p) {
+    parts[p].device = p % ndev;
+    if (std::find(devices.begin(), devices.end(), parts[p].device) == devices.end()) devices.push_back(parts[p].device);
+  }
   auto cleanup = [&] {
-    for (auto& sl : slabs) {
-      sl.lease.release();
-      if (sl.d_flag) { cudaSetDevice(sl.device); cudaFree(sl.d_flag); }
-      if (sl.ctx) sweeptt_destroy(sl.ctx);
+    for (auto& pt : parts) {
+      pt.lease.release();
+      if (pt.ctx) { cudaSetDevice(pt.device); cudaStreamSynchronize(pt.ctx->stream); sweeptt_destroy(pt.ctx); pt.ctx = nullptr; }
     }
+    box_slow.destroy();
+    box_tt.destroy();
   };
-  // ---- build one context per slab: sub-box of the model + halo planes --------------------------
-  for (int d = 0; d < G; ++d) {
-    Slab& sl = slabs[d];
-    sl.device = d % ndev;
-    sl.lo = (int)((long long)n[axis] * d / G);
-    sl.hi = (int)((long long)n[axis] * (d + 1) / G);
-    sl.blo = std::max(0, sl.lo - R);
-    sl.bhi = std::min(n[axis], sl.hi + R);
+  // ---- peer access for the per-part arrays (keys, bounds, state); the shared boxes get theirs from cuMemSetAccess ----
+  for (int a : devices)
+    for (int b : devices) {
+      if (a == b) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, a, b);
+      if (!can) return fail("devices %d and %d cannot access each other's memory", a, b);
+      cudaSetDevice(a);
+      if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();  // (already enabled is fine)
+    }
+  // ---- one context per part, all with the same geometry: kernel x = the caller's slab axis ----
+  BoxGeom g{};
+  for (int p = 0; p < G; ++p) {
+    Part& pt = parts[p];
     sweeptt_opts so = o;
-    so.device = sl.device;
+    so.device = pt.device;
     so.num_devices = 1;
-    sl.ctx = sweeptt_create(&so);
-    if (!sl.ctx) { cleanup(); return 0; }
-    sl.ctx->allow_outside_sources = true;
-    sl.ctx->force_window_axis = 2;  // every slab keeps the caller's axis order
-    int sub[3] = {nx, ny, nz};
-    sub[axis] = sl.bhi - sl.blo;
-    std::vector<float> box((size_t)sub[0] * sub[1] * sub[2]);
-    {
-      int org[3] = {0, 0, 0};
-      org[axis] = sl.blo;
-      if (!fetch(org, sub, box.data())) { cleanup(); return 0; }
-    }
-    START local = start;
-    (axis == 0 ? local.i : axis == 1 ? local.j : local.k) -= sl.blo;
-    if (!sweeptt_set_model(sl.ctx, box.data(), sub[0], sub[1], sub[2]) || !sweeptt_set_star(sl.ctx, fs, starsize) ||
-        !sweeptt_set_sources(sl.ctx, &local, 1) || !sweeptt_reset(sl.ctx)) {
-      cleanup();
-      return 0;
-    }
-    if (sl.ctx->kernel_used != SWEEPTT_KERNEL_TILED) {
-      cleanup();
-      return fail("slab decomposition needs the tiled kernel (star too wide for its halo)");
-    }
-    if (!ready(sl.ctx, &sl.lease)) { cleanup(); return 0; }
-    if (cudaMalloc(&sl.d_flag, sizeof(unsigned)) != cudaSuccess) { cleanup(); return fail("cudaMalloc failed"); }
+    so.kernel = SWEEPTT_KERNEL_TILED;
+    pt.ctx = sweeptt_create(&so);
+    if (!pt.ctx) { cleanup(); return 0; }
+    pt.ctx->force_x_axis = axis;
+    pt.ctx->external_boxes = true;
+    if (!compute_geometry(pt.ctx, nx, ny, nz, &pt.ctx->g)) { cleanup(); return 0; }
+    g = pt.ctx->g;
   }
-  // ---- peer access between neighbouring slabs on different devices (NVLink P2P) ------------------
-  for (int d = 0; d + 1 < G; ++d) {
-    const int a = slabs[d].device, b = slabs[d + 1].device;
-    if (a == b) continue;
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, a, b);
-    if (!can) { cleanup(); return fail("devices %d and %d cannot access each other's memory", a, b); }
-    cudaSetDevice(a); if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
-    cudaSetDevice(b); if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
+  // ownership blocks along kernel x: a few tiles each, dealt round-robin (block-cyclic)
+  int tpb = std::max(1, std::min(4, g.ntx / (4 * G)));
+  if (const char* e = getenv("SWEEPTT_BLOCK_TILES")) tpb = std::max(1, atoi(e));
+  const int nblocks = (g.ntx + tpb - 1) / tpb;
+  for (int b = 0; b < nblocks; ++b) {
+    const int x0 = b * tpb * TX, x1 = std::min(g.nx, (b + 1) * tpb * TX);
+    if (x0 < x1) parts[b % G].blocks.push_back({x0, x1});
   }
+  // memory chunks follow the blocks (rounded to the allocation granularity; a chunk may be empty on small grids)
+  {
+    const VmmApi& v = vmm();
+    if (!v.ok) { cleanup(); return fail("CUDA virtual memory management entry points are not available from this driver"); }
+    size_t gran = 2u << 20;
+    for (int d : devices) {
+      CUmemAllocationProp prop = {};
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = d;
+      size_t gd = 0;
+      if (v.granularity(&gd, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gd > gran) gran = gd;
+    }
+    const size_t plane_bytes = (size_t)g.sx * 4;
+    const size_t total = ((size_t)g.vol * 4 + gran - 1) / gran * gran;
+    std::vector<size_t> cuts;
+    std::vector<int> chunk_dev;
+    for (int b = 0; b < nblocks; ++b) {
+      const size_t first_plane = b == 0 ? 0 : (size_t)b * tpb * TX + AX;  // padded plane index where the block starts
+      cuts.push_back(std::min(total, first_plane * plane_bytes / gran * gran));
+      chunk_dev.push_back(parts[b % G].device);
+    }
+    cuts.push_back(total);
+    for (int d : devices) { cudaSetDevice(d); cudaFree(0); }  // primary contexts exist before memory is placed
+    if (!box_slow.create(cuts, chunk_dev, devices) || !box_tt.create(cuts, chunk_dev, devices)) { cleanup(); return 0; }
+  }
+  int R = 0;
+  for (int l = 0; l < starsize; ++l) R = std::max(R, std::abs(axis == 0 ? fs[l].i : axis == 1 ? fs[l].j : fs[l].k));
+  (void)R;
 
-  // ---- outer loop: K relaxation rounds on every slab concurrently, then halo exchange -----------
-  // (K small: the front crosses slab boundaries while all slabs keep working; waiting for local
-  //  convergence before exchanging would serialise the slabs behind the one that holds the source)
+  // ---- set-up, upload, solve and gather run in one host thread per part ----
+  const auto t_begin = std::chrono::steady_clock::now();
+  std::chrono::steady_clock::time_point t_solve0, t_solve1, t_end;
+  PhaseBarrier bar(G);
+  Quiescence quiet(G);
+  const int K = o.rounds_per_poll > 0 ? o.rounds_per_poll : 4;
+  float* const d_slow = reinterpret_cast<float*>(box_slow.va);
+  float* const d_tt = reinterpret_cast<float*>(box_tt.va);
+  const float INF = std::numeric_limits<float>::infinity();
+  std::atomic<int> setup_failed{0};
+  std::vector<long long> batches(G, 0);
+
+  auto part_main = [&](int p) {
+    Part& pt = parts[p];
+    sweeptt_ctx* c = pt.ctx;
+    auto bail = [&](const char* what) { pt.ok = 0; pt.err = std::string(what) + ": " + g_err; setup_failed = 1; };
+#define PCK(call)                                                                                       \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess && pt.ok) { pt.ok = 0; pt.err = std::string(#call) + ": " + cudaGetErrorString(e__); setup_failed = 1; } \
+  } while (0)
+    PCK(cudaSetDevice(pt.device));
+    // phase 1: +INF into the pages this part's DEVICE holds (both boxes: apron and not-yet-uploaded nodes)
+    for (const SharedBox* sb : {&box_slow, &box_tt})
+      for (const auto& ch : sb->chunks) {
+        // chunks of one device are filled by the first part on that device
+        int first = -1;
+        for (int q = 0; q < G && first < 0; ++q) if (parts[q].device == ch.device) first = q;
+        if (first != p) continue;
+        PCK(launch_fill(reinterpret_cast<float*>(sb->va + ch.off), (long long)(ch.size / 4), INF, c->stream));
+      }
+    PCK(cudaStreamSynchronize(c->stream));
+    bar.wait();
+    // phase 2: upload the owned blocks of the model (sub-box in caller order -> padded shared box)
+    c->d_slow = d_slow; c->d_tt = d_tt; c->tt_cap = 1;
+    c->have_model = true;
+    if (pt.ok && !setup_failed) {
+      size_t stage_floats = 0;
+      for (auto& b : pt.blocks) {
+        int sub[3] = {nx, ny, nz};
+        sub[axis] = b.second - b.first;
+        stage_floats = std::max(stage_floats, (size_t)sub[0] * sub[1] * sub[2]);
+      }
+      float* h_stage = nullptr;
+      if (stage_floats && (!ensure_stage(c, stage_floats) || cudaMallocHost(&h_stage, stage_floats * 4) != cudaSuccess)) bail("staging");
+      for (auto& b : pt.blocks) {
+        if (!pt.ok) break;
+        int sub[3] = {nx, ny, nz}, org[3] = {0, 0, 0};
+        sub[axis] = b.second - b.first;
+        org[axis] = b.first;
+        const size_t cnt = (size_t)sub[0] * sub[1] * sub[2];
+        if (!fetch(org, sub, h_stage)) { bail("reading the model"); break; }
+        PCK(cudaMemcpyAsync(c->d_stage, h_stage, cnt * 4, cudaMemcpyHostToDevice, c->stream));
+        BoxGeom gs = g;
+        gs.nx = b.second - b.first;
+        const long long ds[3] = {(long long)sub[1] * sub[2], (long long)sub[2], 1};
+        for (int q = 0; q < 3; ++q) gs.dstride[q] = ds[g.perm[q]];
+        PCK(launch_pad_box(c->d_stage, d_slow + (size_t)b.first * g.sx, gs, c->stream));
+        unsigned r[6] = {0, 0, 0, 0, 0, 0};
+        PCK(launch_min_slowness(c->d_stage, (long long)cnt, reinterpret_cast<unsigned*>(c->d_viol), c->stream));
+        PCK(cudaMemcpyAsync(r, c->d_viol, sizeof r, cudaMemcpyDeviceToHost, c->stream));
+        PCK(cudaStreamSynchronize(c->stream));
+        float vmin; double sum; unsigned long long cn;
+        std::memcpy(&vmin, &r[0], 4); std::memcpy(&sum, &r[2], 8); std::memcpy(&cn, &r[4], 8);
+        if (r[1]) pt.bad_slow = true;
+        pt.min_slow = std::min(pt.min_slow, (double)vmin);
+        pt.sum_slow += sum; pt.cnt_slow += cn;
+      }
+      if (h_stage) cudaFreeHost(h_stage);
+    }
+    bar.wait();
+    // phase 3: model statistics are global; star, start point, per-part scheduling arrays
+    if (pt.ok && !setup_failed) {
+      double mn = std::numeric_limits<double>::infinity(), sum = 0;
+      unsigned long long cn = 0;
+      bool bad = false;
+      for (auto& q : parts) { mn = std::min(mn, q.min_slow); sum += q.sum_slow; cn += q.cnt_slow; bad = bad || q.bad_slow; }
+      if (bad) { fail("the model holds negative or NaN slowness values"); bail("model"); }
+      c->min_slowness = std::isfinite(mn) ? (float)mn : -1.f;
+      c->mean_slowness = cn ? sum / (double)cn : 0.0;
+      c->allow_outside_sources = false;
+      if (pt.ok && (!sweeptt_set_star(c, fs, starsize) || !sweeptt_set_sources(c, &start, 1))) bail("star / start point");
+      if (pt.ok && c->kernel_used != SWEEPTT_KERNEL_TILED) { fail("one grid over several devices needs the tiled kernel (star too wide for its halo)"); bail("kernel"); }
+    }
+    bar.wait();
+    // phase 4: everybody's arrays exist -> exchange the pointers, take the constant tables, reset
+    if (pt.ok && !setup_failed) {
+      c->mp_nparts = G; c->mp_part = p; c->mp_tiles_per_block = tpb;
+      for (int q = 0; q < G; ++q) {
+        c->mp_key[q] = parts[q].ctx->d_key;
+        c->mp_tmax[q] = parts[q].ctx->d_tmax;
+        c->mp_kmin[q] = &parts[q].ctx->d_state->kmin_pub;
+      }
+      if (!ready(c, &pt.lease)) bail("ready");
+      if (pt.ok) PCK(launch_reset_part(make_args(c), o.max_rounds, c->stream));
+      PCK(cudaStreamSynchronize(c->stream));
+    }
+    bar.wait();
+    if (p == 0) t_solve0 = std::chrono::steady_clock::now();
+    // phase 5: first work lists, then batches of K rounds until the job is quiescent
+    if (pt.ok && !setup_failed) {
+      PCK(launch_init_sources(make_args(c), c->stream));
+      long long last_visits = 0;
+      while (pt.ok) {
+        int changed = 0;
+        if (!run_rounds(c, false, K, &changed, nullptr)) { pt.ok = 0; pt.err = g_err; quiet.abort(); break; }
+        batches[p] += 1;
+        const SolveState& h = *c->h_state;
+        const bool pending = h.count[h.parity] != 0 || h.kmin_pub != 0x7f800000u;
+        const bool worked = (long long)h.tile_visits != last_visits;
+        last_visits = (long long)h.tile_visits;
+        if (quiet.report(p, last_visits, !pending && !worked)) break;
+        if (o.max_rounds > 0 && h.round >= o.max_rounds) { pt.ok = 0; pt.err = "not converged after max_rounds"; quiet.abort(); break; }
+      }
+    } else {
+      quiet.abort();
+    }
+    bar.wait();
+    if (p == 0) t_solve1 = std::chrono::steady_clock::now();
+    // phase 6: gather the owned blocks
+    if (pt.ok && !setup_failed && !quiet.failed) {
+      float* h_stage = nullptr;
+      size_t stage_floats = 0;
+      for (auto& b : pt.blocks) {
+        int sub[3] = {nx, ny, nz};
+        sub[axis] = b.second - b.first;
+        stage_floats = std::max(stage_floats, (size_t)sub[0] * sub[1] * sub[2]);
+      }
+      if (stage_floats && axis != 0 && cudaMallocHost(&h_stage, stage_floats * 4) != cudaSuccess) bail("staging");
+      for (auto& b : pt.blocks) {
+        if (!pt.ok) break;
+        int sub[3] = {nx, ny, nz};
+        sub[axis] = b.second - b.first;
+        const size_t cnt = (size_t)sub[0] * sub[1] * sub[2];
+        BoxGeom gs = g;
+        gs.nx = b.second - b.first;
+        const long long ds[3] = {(long long)sub[1] * sub[2], (long long)sub[2], 1};
+        for (int q = 0; q < 3; ++q) gs.dstride[q] = ds[g.perm[q]];
+        PCK(launch_unpad_box(d_tt + (size_t)b.first * g.sx, c->d_stage, gs, c->stream));
+        if (axis == 0) {  // planes of the caller's slowest axis are contiguous in the caller's box
+          PCK(cudaMemcpyAsync(tt_out + (size_t)b.first * ny * nz, c->d_stage, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+          PCK(cudaStreamSynchronize(c->stream));
+        } else {
+          PCK(cudaMemcpyAsync(h_stage, c->d_stage, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+          PCK(cudaStreamSynchronize(c->stream));
+          for (int x = 0; x < sub[0]; ++x)
+            for (int y = 0; y < sub[1]; ++y) {
+              const size_t src = ((size_t)x * sub[1] + y) * sub[2];
+              if (axis == 1)
+                std::memcpy(tt_out + ((size_t)x * ny + (y + b.first)) * nz, h_stage + src, sizeof(float) * sub[2]);
+              else
+                std::memcpy(tt_out + ((size_t)x * ny + y) * nz + b.first, h_stage + src, sizeof(float) * sub[2]);
+            }
+        }
+      }
+      if (h_stage) cudaFreeHost(h_stage);
+    }
+#undef PCK
+  };
+  {
+    std::vector<std::thread> th;
+    for (int p = 0; p < G; ++p) th.emplace_back(part_main, p);
+    for (auto& t : th) t.join();
+  }
+  t_end = std::chrono::steady_clock::now();
+  for (int p = 0; p < G; ++p)
+    if (!parts[p].ok) {
+      const std::string e = parts[p].err;
+      cleanup();
+      return fail("part %d: %s", p, e.c_str());
+    }
+  if (setup_failed || quiet.failed) { cleanup(); return fail("one grid over several devices: a part failed"); }
+
   sweeptt_stats total{};
   total.struct_size = sizeof total;
-  const auto t0 = std::chrono::steady_clock::now();
-  const int K = o.rounds_per_poll > 0 ? o.rounds_per_poll : 8;
-  int outer = 0;
-  for (;; ++outer) {
-    std::vector<std::thread> th;
-    std::vector<int> pending(G, 0);
-    for (int d = 0; d < G; ++d)
-      th.emplace_back([&, d] {
-        Slab& sl = slabs[d];
-        if (cudaSetDevice(sl.device) != cudaSuccess) { sl.ok = 0; sl.err = "cudaSetDevice failed"; return; }
-        int changed = 0;
-        sl.ok = run_rounds(sl.ctx, false, K, &changed, &sl.st);
-        pending[d] = changed;
-        if (!sl.ok) sl.err = g_err;
-      });
-    for (auto& t : th) t.join();
-    for (int d = 0; d < G; ++d)
-      if (!slabs[d].ok) { const std::string e = slabs[d].err; cleanup(); return fail("slab %d: %s", d, e.c_str()); }
-    // exchange: each side min-merges the neighbour's owned boundary planes into its halo
-    for (int d = 0; d < G; ++d) {
-      cudaSetDevice(slabs[d].device);
-      CK(cudaMemsetAsync(slabs[d].d_flag, 0, sizeof(unsigned), slabs[d].ctx->stream));
-    }
-    for (int d = 0; d + 1 < G; ++d) {
-      Slab& A = slabs[d];      // owns planes below the interface at A.hi == B.lo
-      Slab& B = slabs[d + 1];
-      const int up = A.bhi - A.hi;   // A's halo planes above the interface (owned by B)
-      const int dn = B.lo - B.blo;   // B's halo planes below the interface (owned by A)
-      if (up > 0) {
-        cudaSetDevice(A.device);
-        CK(launch_merge_halo(make_args(A.ctx), B.ctx->d_tt, B.ctx->g, axis, A.hi - A.blo, up, A.hi - B.blo, A.d_flag,
-                             A.ctx->stream));
-      }
-      if (dn > 0) {
-        cudaSetDevice(B.device);
-        CK(launch_merge_halo(make_args(B.ctx), A.ctx->d_tt, A.ctx->g, axis, 0, dn, B.blo - A.blo, B.d_flag,
-                             B.ctx->stream));
-      }
-    }
-    unsigned any = 0;
-    for (int d = 0; d < G; ++d) {
-      unsigned f = 0;
-      cudaSetDevice(slabs[d].device);
-      CK(cudaMemcpyAsync(&f, slabs[d].d_flag, sizeof f, cudaMemcpyDeviceToHost, slabs[d].ctx->stream));
-      CK(cudaStreamSynchronize(slabs[d].ctx->stream));
-      any |= f;
-      any |= (unsigned)pending[d];
-    }
-    if (o.verbose > 0) fprintf(stderr, "[sweeptt] slab exchange %d: %s\n", outer, any ? "work pending" : "converged");
-    if (!any) break;  // every slab drained its work list and no halo was lowered: global fixed point
-    if (o.max_rounds > 0 && outer * K >= o.max_rounds) { cleanup(); return fail("slabs not converged after %d rounds", outer * K); }
+  for (int p = 0; p < G; ++p) {
+    sweeptt_ctx* c = parts[p].ctx;
+    cudaSetDevice(parts[p].device);
+    read_state(c);
+    total.relaxations += (long long)c->h_state->pulls;
+    total.tile_visits += (long long)c->h_state->tile_visits;
+    total.units_run += (long long)c->h_state->units_run;
+    total.units_changed += (long long)c->h_state->units_changed;
+    total.rounds = std::max(total.rounds, c->h_state->round);
+    total.kernel_launches += 3LL * c->h_state->round;
+    total.relax_launches += c->h_state->round;
   }
-  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-
-  // ---- gather the owned planes --------------------------------------------------------------------
-  for (int d = 0; d < G; ++d) {
-    Slab& sl = slabs[d];
-    int sub[3] = {nx, ny, nz};
-    sub[axis] = sl.bhi - sl.blo;
-    std::vector<float> box((size_t)sub[0] * sub[1] * sub[2]);
-    cudaSetDevice(sl.device);
-    if (!sweeptt_get_tt(sl.ctx, 0, box.data())) { cleanup(); return 0; }
-    for (int x = 0; x < sub[0]; ++x)
-      for (int y = 0; y < sub[1]; ++y) {
-        const int gx = x + (axis == 0 ? sl.blo : 0), gy = y + (axis == 1 ? sl.blo : 0);
-        if ((axis == 0 && (gx < sl.lo || gx >= sl.hi)) || (axis == 1 && (gy < sl.lo || gy >= sl.hi))) continue;
-        const int z0 = axis == 2 ? sl.lo - sl.blo : 0, zn = axis == 2 ? sl.hi - sl.lo : sub[2];
-        std::memcpy(tt_out + gx * stride[0] + gy * stride[1] + (axis == 2 ? sl.lo : 0),
-                    &box[((size_t)x * sub[1] + y) * sub[2] + z0], sizeof(float) * zn);
-      }
-    // the context counters are cumulative since the reset: read the final totals
-    read_state(sl.ctx);
-    total.relaxations += (long long)sl.ctx->h_state->pulls;
-    total.tile_visits += (long long)sl.ctx->h_state->tile_visits;
-    total.rounds = std::max(total.rounds, sl.ctx->h_state->round);
-    total.kernel_launches += 3LL * sl.ctx->h_state->round + 2LL * (outer + 1);
-    total.relax_launches += sl.ctx->h_state->round;
-  }
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
   total.kernel_used = SWEEPTT_KERNEL_TILED;
-  total.devices_used = std::min(G, ndev);
-  total.solve_ms = ms;
+  total.devices_used = (int)devices.size();
+  total.solve_ms = ms(t_solve0, t_solve1);
+  total.h2d_ms = ms(t_begin, t_solve0);
+  total.d2h_ms = ms(t_solve1, t_end);
+  total.h2d_bytes = (long long)nx * ny * nz * 4;
+  total.d2h_bytes = (long long)nx * ny * nz * 4;
+  if (o.verbose > 0) {
+    fprintf(stderr, "[sweeptt] one grid over %d parts (%zu devices), %d blocks of %d tiles: set-up %.1f ms, solve %.1f ms, gather %.1f ms; batches per part:",
+            G, devices.size(), nblocks, tpb, total.h2d_ms, total.solve_ms, total.d2h_ms);
+    for (int p = 0; p < G; ++p) fprintf(stderr, " %lld", batches[p]);
+    fprintf(stderr, "\n");
+  }
   if (stats) *stats = total;
   cleanup();
   return 1;
