@@ -87,6 +87,8 @@ def test_more_sources_than_one_launch_holds_run_as_waves_of_single_launches(monk
     assert va == [0] * 5 and vb == [0] * 5
     for s in range(5):
         assert_bit_equal(a[s], b[s], f"source {s}: waves vs rounds")
+    monkeypatch.delenv("SWEEPTT_WAVE", raising=False)
+    monkeypatch.setenv("SWEEPTT_PERSIST", "1")
     monkeypatch.setenv("SWEEPTT_PERSIST_MAX_KEYS", str(2 * ntiles + 1))
     c, sc = P.solve(v, off, starts, kernel=api.KERNEL_TILED)
     assert sc.relax_launches == 3 and sc.d2h_bytes == 5 * v.size * 4

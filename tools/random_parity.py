@@ -21,11 +21,27 @@ for seed in range(first, first + count):
     dims, v, off, starts, label = _case(rng)
     knobs = {"SWEEPTT_BUCKET": rng.choice(["-1", "0.5", "2", "8"]), "SWEEPTT_GROUPS": rng.choice(["1", "2", "3"]),
              "SWEEPTT_PERSIST": rng.choice(["0", "1"]), "SWEEPTT_LOOKAHEAD": rng.choice(["0", "0.03", "4"]),
-             "SWEEPTT_INNER": rng.choice(["1", "2", "3"]), "SWEEPTT_TRIGGER_FRAC": rng.choice(["0", "0.4", "0.9"])}
+             "SWEEPTT_INNER": rng.choice(["1", "2", "3"]), "SWEEPTT_TRIGGER_FRAC": rng.choice(["0", "0.4", "0.9"]),
+             "SWEEPTT_WAVE": rng.choice(["0", "1", "2", "64"]), "SWEEPTT_WAVE_STREAMS": rng.choice(["1", "2"]),
+             "SWEEPTT_BLOCK_TILES": rng.choice(["1", "2", "4"])}
     os.environ.update({k: str(x) for k, x in knobs.items()})
     kernel = int(rng.choice([api.KERNEL_AUTO, api.KERNEL_AUTO, api.KERNEL_SIMPLE]))
     loop = int(rng.choice([api.LOOP_GRAPH, api.LOOP_GRAPH, api.LOOP_BATCHED]))
     tt, st = P.solve(v, off, starts, kernel=kernel, loop=loop)
+    grid_parts = int(rng.integers(1, 6))
+    grid_axis = int(rng.integers(0, 3))
+    if seed % 3 == 0 and max(abs(off).max(axis=0)[:2]) <= 7 and abs(off).max() <= 7 and grid_parts <= dims[grid_axis]:
+        # ONE grid over several parts (they share the visible devices): same bits as the multi-start path
+        try:
+            one, _ = P.solve_slabs(v, off, starts[0], num_slabs=grid_parts, slab_axis=grid_axis)
+            nd = int((one.view(np.uint32) != tt[0].view(np.uint32)).sum())
+        except P.SweepError as e:
+            nd = 0 if "tiled kernel" in str(e) else -1
+            if nd:
+                print("one-grid error:", e, flush=True)
+        if nd:
+            bad += 1
+            print(f"MISMATCH (one grid, {grid_parts} parts, axis {grid_axis}) seed {seed}: {label} knobs={knobs}: {nd} floats", flush=True)
     for s, p in enumerate(starts):
         ref, _, _ = oracle.solve(v, off, p)
         nd = int((ref.view(np.uint32) != tt[s].view(np.uint32)).sum())

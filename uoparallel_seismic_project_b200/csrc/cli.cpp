@@ -13,6 +13,7 @@
 // slabs over the GPUs, single start point files only), SWEEPTT_TT_BIN=path
 // (also dump raw float32 fields), SWEEPTT_NO_OUTPUT=1 (skip output.tt), SWEEPTT_KERNEL=simple.
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +103,7 @@ int main(int argc, char* argv[]) {
   if (const char* e = std::getenv("SWEEPTT_DEVICES")) opts.num_devices = std::atoi(e);
   if (const char* e = std::getenv("SWEEPTT_KERNEL")) opts.kernel = !std::strcmp(e, "simple") ? SWEEPTT_KERNEL_SIMPLE : SWEEPTT_KERNEL_AUTO;
   sweeptt_stats st;
+  const auto t_solve0 = std::chrono::steady_clock::now();
   std::printf("sweep 1 begin\n");
   std::fflush(stdout);
   int ok;
@@ -130,11 +132,20 @@ int main(int argc, char* argv[]) {
       std::fclose(f);
     }
   }
+  const auto t_solve1 = std::chrono::steady_clock::now();
   if (!std::getenv("SWEEPTT_NO_OUTPUT")) {
     if (!sweeptt_write_output_tt("output.tt", tt.data(), numstart, nx, ny, nz)) {
       std::printf("Can not open travel time output file: %s\n", "output.tt");
       return 1;
     }
+  }
+  if (std::getenv("SWEEPTT_TIMING")) {  // phase times of the whole command (stderr: stdout keeps the reference's lines)
+    const auto t_end = std::chrono::steady_clock::now();
+    auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double>(b - a).count();
+    };
+    std::fprintf(stderr, "[sweeptt-timing] solve_call_s=%.4f output_tt_s=%.4f sources=%d nodes=%zu\n", sec(t_solve0, t_solve1),
+                 sec(t_solve1, t_end), numstart, vol);
   }
   for (int s = 0; s < numstart; ++s) std::free(tt[s]);
   sweeptt_free(slow);

@@ -38,6 +38,23 @@
 #include <cstdint>
 #include <limits>
 
+// -DSWEEPTT_DEBUG_BOUNDS: every TMA coordinate, shared-memory window index, min-cell index, work-list entry and
+// result address of the tiled kernel is checked on the device (printf + trap).  compute-sanitizer is not available
+// on the GPU pool, so this build run over the random parity cases (tools/debug_bounds.py) is its stand-in.
+#ifdef SWEEPTT_DEBUG_BOUNDS
+#include <cstdio>
+#define DBG_BOUNDS(cond)                                                                                        \
+  do {                                                                                                          \
+    if (!(cond)) {                                                                                              \
+      printf("sweeptt bounds check failed: %s (kernels.cu:%d, block %d, thread %d)\n", #cond, __LINE__, (int)blockIdx.x, \
+             (int)(threadIdx.y * blockDim.x + threadIdx.x));                                                    \
+      __trap();                                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define DBG_BOUNDS(cond) do { } while (0)
+#endif
+
 namespace sweeptt {
 
 // ---------------------------------------------------------------------------------------
@@ -342,13 +359,30 @@ __device__ __forceinline__ void run_pattern_range(const float* __restrict__ sv, 
 template <typename HOOK, uint32_t... M>
 __device__ __forceinline__ void columns_phase(MaskList<M...>, const float* __restrict__ sv,
                                               const float* __restrict__ st, int b0, const RelaxArgs& a, int f0,
-                                              const float (&vn)[KZ], float (&acc)[KZ], HOOK&& after) {
+                                              const float (&vn)[KZ], float (&acc)[KZ], HOOK&& after, int dbg_box_floats) {
+  (void)dbg_box_floats;
   u64 vnE[KZ / 2], vnO[KZ / 2 - 1];
 #pragma unroll
   for (int j = 0; j < KZ / 2; ++j) vnE[j] = pack2(vn[2 * j], vn[2 * j + 1]);
 #pragma unroll
   for (int j = 0; j < KZ / 2 - 1; ++j) vnO[j] = lds_pair_keep(sv + b0 + ZHALO + 2 * j + 1);  // = (vn[2j+1], vn[2j+2])
   const u64 nz2 = pack2(a.neg_zero, a.neg_zero);
+#ifdef SWEEPTT_DEBUG_BOUNDS
+  {  // every window this warp is going to read lies inside the staged box; every half-distance inside its table
+    const int ngroups = sizeof...(M) == 0 ? a.npat : (int)sizeof...(M);
+    DBG_BOUNDS(ngroups <= MAX_PATTERNS && f0 >= 0 && f0 + (ngroups - 1) * MAX_WARPS < NXCLASS * 6 * MAX_PATTERNS * MAX_WARPS);
+    for (int g = 0; g < ngroups; ++g) {
+      const unsigned d = c_pdesc[g * MAX_WARPS + f0];
+      const int lo = (int)(d & 511u), hi_ = (int)((d >> 9) & 511u);
+      DBG_BOUNDS(lo <= hi_ && hi_ <= a.ncols && a.ncols <= MAX_COLUMNS);
+      for (int c = lo; c < hi_; ++c) {
+        const ColumnDev col = c_cols[c];
+        DBG_BOUNDS(b0 + col.soff >= 0 && b0 + col.soff + WIN <= dbg_box_floats);
+        DBG_BOUNDS(col.hd_begin >= 0 && col.hd_begin + __popc(col.kmask) <= MAX_COL_HD);
+      }
+    }
+  }
+#endif
   if constexpr (sizeof...(M) == 0) {
     // generic: runtime masks (any star that fits the halo)
     float W[WIN], T[WIN];  // granules a column does not touch keep stale, never-read values
@@ -556,6 +590,10 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int ty = tp % a.g.nty;
     const int tx = tp / a.g.nty;
     float* sv = ring + q * 2 * D::BOX_STRIDE;
+    DBG_BOUNDS(tile >= 0 && s >= 0 && s < a.nsrc && tx >= 0 && tx < a.g.ntx);
+    DBG_BOUNDS(tz * TZ + AZ - ZHALO >= 0 && tz * TZ + AZ - ZHALO + SZD <= a.g.pz);
+    DBG_BOUNDS(ty * TY + AY - RXY >= 0 && ty * TY + AY - RXY + D::SYD <= a.g.py);
+    DBG_BOUNDS(tx * TX + AX - RXY >= 0 && tx * TX + AX - RXY + D::SXD <= a.g.px);
     // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
     mbar_expect_tx(&full[q], 2u * sizeof(float) * D::BOX_FLOATS);
     tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY);
@@ -669,7 +707,12 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int P = NW / nlive;
     const int unit = wq / P, part = wq - unit * P;
     const int xc = tx == 0 ? 1 : (tx == a.g.ntx - 1 ? 2 : 0);  // tile position along x: which columns can reach the grid at all
-    const int f0 = ((xc * 6 + (PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
+    int f0 = ((xc * 6 + (PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
+    // keep the index in ONE register: left alone, ptxas re-derives it (unit / part / table selects, 9 instructions)
+    // in front of every one of the 18 pattern blocks of every tile
+#ifndef SWEEPTT_NO_PIN
+    asm volatile("" : "+r"(f0));
+#endif
     const bool owner = part == 0;
     const int x = (unit << 2) | (lane >> 3);
     // smem float index of this thread's window start for the (0,0) column
@@ -677,6 +720,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int gx = x0 + x, gy = y0 + y, gz = z0;
     const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
     unsigned* cell = s_acc + ((q * UNITS + unit) * KZ) * 32 + lane;  // cell[k * 32]
+    DBG_BOUNDS(((q * UNITS + unit) * KZ + KZ - 1) * 32 + lane < D::ACC_WORDS && unit < UNITS);
+    DBG_BOUNDS(b0 + ZHALO >= 0 && b0 + ZHALO + KZ <= D::BOX_FLOATS);
     float vn[KZ], acc[KZ];
 #pragma unroll
     for (int j = 0; j < KZ / 4; ++j) {
@@ -734,7 +779,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             if (g == h1) stage_tile(q ^ 1, next_tile);
           }
         }
-      });
+      }, D::BOX_FLOATS);
       float bq[KZ];
 #pragma unroll
       for (int j = 0; j < KZ / 4; ++j) {
@@ -811,6 +856,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         if (lowered & (1u << k)) tmin = fminf(tmin, acc[k]);
       if (changed) {
         float* out = a.tt + (size_t)s * a.g.vol + ((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ);
+        DBG_BOUNDS(gx < a.g.nx && gy < a.g.ny && gz < a.g.nz);  // only nodes inside the grid are ever lowered
+        DBG_BOUNDS(((size_t)(gx + AX) * a.g.py + (gy + AY)) * a.g.pz + (gz + AZ) + KZ <= (size_t)a.g.vol);
 #pragma unroll
         for (int j = 0; j < KZ / 4; ++j)
           *reinterpret_cast<float4*>(out + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
