@@ -143,6 +143,13 @@ int sweeptt_solve(const float *slowness, int nx, int ny, int nz, const struct FS
                   const struct START *starts, int numstart, float *const *tt_out,
                   const sweeptt_opts *opts, sweeptt_stats *stats);
 
+/* Page-locked host memory for the boxes handed to sweeptt_solve (the counterpart of boxalloc's malloc,
+ * include/floatbox.h:122-123): with such buffers the device->host copies of finished sources run at PCIe speed
+ * BEHIND the relaxation of the remaining ones; pageable memory works too, only slower (the driver stages it).
+ * Returns NULL on failure.  Release with sweeptt_host_free. */
+void *sweeptt_host_alloc(size_t bytes);
+void sweeptt_host_free(void *p);
+
 /* sweeptt_solve keeps one cached context (device boxes, star tables) per device between
  * calls -- the device-resident float-box pool; this releases them. */
 void sweeptt_release_cache(void);

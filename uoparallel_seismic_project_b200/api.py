@@ -86,6 +86,7 @@ def lib_path() -> pathlib.Path:
 _EXPORTS = [
     "sweeptt_device_count", "sweeptt_device_info", "sweeptt_last_error", "sweeptt_version",
     "sweeptt_star_fill_distances", "sweeptt_build_pull_star", "sweeptt_debug_column_split", "sweeptt_solve", "sweeptt_release_cache",
+    "sweeptt_host_alloc", "sweeptt_host_free",
     "sweeptt_create", "sweeptt_destroy", "sweeptt_set_stream", "sweeptt_set_model", "sweeptt_set_star",
     "sweeptt_set_sources", "sweeptt_run", "sweeptt_step", "sweeptt_reset", "sweeptt_get_tt", "sweeptt_put_tt",
     "sweeptt_count_violations", "sweeptt_relaxations_per_round", "sweeptt_pool_bytes", "sweeptt_tiles_per_source", "sweeptt_solve_slabs",
@@ -115,6 +116,10 @@ def load_library() -> C.CDLL:
     lib.sweeptt_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FS), C.c_int, C.POINTER(START),
                                   C.c_int, C.POINTER(C.c_void_p), C.POINTER(_Opts), C.POINTER(_Stats)]
     lib.sweeptt_release_cache.restype = None
+    lib.sweeptt_host_alloc.argtypes = [C.c_size_t]
+    lib.sweeptt_host_alloc.restype = C.c_void_p
+    lib.sweeptt_host_free.argtypes = [C.c_void_p]
+    lib.sweeptt_host_free.restype = None
     lib.sweeptt_create.argtypes = [C.POINTER(_Opts)]
     lib.sweeptt_create.restype = C.c_void_p
     lib.sweeptt_destroy.argtypes = [C.c_void_p]

@@ -89,8 +89,12 @@ int main(int argc, char* argv[]) {
 
   const size_t vol = (size_t)nx * ny * nz;
   std::vector<float*> tt(numstart);
+  std::vector<char> pinned(numstart, 0);
   for (int s = 0; s < numstart; ++s) {
-    tt[s] = static_cast<float*>(std::malloc(vol * sizeof(float)));
+    // boxalloc (include/floatbox.h:122-123) -- page-locked when possible, so the copies back overlap the solve
+    tt[s] = static_cast<float*>(sweeptt_host_alloc(vol * sizeof(float)));
+    pinned[s] = tt[s] != nullptr;
+    if (!tt[s]) tt[s] = static_cast<float*>(std::malloc(vol * sizeof(float)));
     if (!tt[s]) {
       std::printf("out of memory for travel time volume %d\n", s);
       return 1;
@@ -147,7 +151,9 @@ int main(int argc, char* argv[]) {
     std::fprintf(stderr, "[sweeptt-timing] solve_call_s=%.4f output_tt_s=%.4f sources=%d nodes=%zu\n", sec(t_solve0, t_solve1),
                  sec(t_solve1, t_end), numstart, vol);
   }
-  for (int s = 0; s < numstart; ++s) std::free(tt[s]);
+  for (int s = 0; s < numstart; ++s) {
+    if (pinned[s]) sweeptt_host_free(tt[s]); else std::free(tt[s]);
+  }
   sweeptt_free(slow);
   sweeptt_free(fs);
   sweeptt_free(starts);

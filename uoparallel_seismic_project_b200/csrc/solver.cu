@@ -901,10 +901,11 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.neg_zero = -0.0f;
   a.max_inner = c->max_inner;
   a.nparts = c->mp_nparts; a.part = c->mp_part; a.tiles_per_block = std::max(1, c->mp_tiles_per_block);
+  static const bool own_front = getenv("SWEEPTT_NO_GLOBAL_KMIN") != nullptr;  // (experiment: every part follows its own front)
   for (int q = 0; q < MAX_PARTS; ++q) {
     a.part_key[q] = c->mp_key[q];
     a.part_tmax[q] = a.tmax ? c->mp_tmax[q] : nullptr;
-    a.part_kmin[q] = c->mp_kmin[q];
+    a.part_kmin[q] = own_front ? c->mp_kmin[c->mp_part] : c->mp_kmin[q];
   }
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   a.npat = (int)c->pat_begin.size() - 1;
@@ -1571,6 +1572,15 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
   return 1;
 }
 
+extern "C" void* sweeptt_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (sweeptt_device_count() <= 0) { fail("no CUDA device available"); return nullptr; }
+  const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); fail("cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+extern "C" void sweeptt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int sweeptt_solve(const float* slowness, int nx, int ny, int nz, const struct FS* fs, int starsize,
                              const struct START* starts, int numstart, float* const* tt_out, const sweeptt_opts* opts,
                              sweeptt_stats* stats) {
@@ -1901,7 +1911,8 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   float* const d_tt = reinterpret_cast<float*>(box_tt.va);
   const float INF = std::numeric_limits<float>::infinity();
   std::atomic<int> setup_failed{0};
-  std::vector<long long> batches(G, 0);
+  std::vector<long long> batches(G, 0), idle_batches(G, 0);
+  std::vector<double> busy_ms(G, 0.0);
 
   auto part_main = [&](int p) {
     Part& pt = parts[p];
@@ -1996,11 +2007,14 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
       long long last_visits = 0;
       while (pt.ok) {
         int changed = 0;
+        const auto tb0 = std::chrono::steady_clock::now();
         if (!run_rounds(c, false, K, &changed, nullptr)) { pt.ok = 0; pt.err = g_err; quiet.abort(); break; }
         batches[p] += 1;
         const SolveState& h = *c->h_state;
         const bool pending = h.count[h.parity] != 0 || h.kmin_pub != 0x7f800000u;
         const bool worked = (long long)h.tile_visits != last_visits;
+        if (worked) busy_ms[p] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+        else idle_batches[p] += 1;
         last_visits = (long long)h.tile_visits;
         if (quiet.report(p, last_visits, !pending && !worked)) break;
         if (o.max_rounds > 0 && h.round >= o.max_rounds) { pt.ok = 0; pt.err = "not converged after max_rounds"; quiet.abort(); break; }
@@ -2091,7 +2105,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   if (o.verbose > 0) {
     fprintf(stderr, "[sweeptt] one grid over %d parts (%zu devices), %d blocks of %d tiles: set-up %.1f ms, solve %.1f ms, gather %.1f ms; batches per part:",
             G, devices.size(), nblocks, tpb, total.h2d_ms, total.solve_ms, total.d2h_ms);
-    for (int p = 0; p < G; ++p) fprintf(stderr, " %lld", batches[p]);
+    for (int p = 0; p < G; ++p) fprintf(stderr, " %lld (%lld without work, %.1f ms in batches with work, %lld tiles)", batches[p], idle_batches[p], busy_ms[p], (long long)parts[p].ctx->h_state->tile_visits);
     fprintf(stderr, "\n");
   }
   if (stats) *stats = total;
