@@ -583,6 +583,19 @@ def run_ours(args):
             "algorithmic_bytes_per_launch": alg_bytes_per_launch,
         },
     }
+    try:   # the reference's OWN CUDA programs timed on a B200 of this pool (tools/legacy_gpu.py; a cited measurement)
+        lg = json.loads((ROOT / "profiles" / "r02_legacy_gpu.json").read_text())
+        line["legacy_gpu"] = {
+            "source": "profiles/r02_legacy_gpu.json (tools/legacy_gpu.py: cuda/cudasweep-tt-multistart_230.cu and _380.cu compiled "
+                      "unmodified with nvcc -arch=sm_100, config 2, same pool's B200; not re-run inside bench.py)",
+            "ms_per_converged_source": {k: v.get("ms_per_converged_source_mean") for k, v in lg["variants"].items()},
+            "kernel_ms_per_sweep": {k: v.get("kernel_ms_per_sweep_mean") for k, v in lg["variants"].items()},
+            "sweeps_per_source": {k: v.get("sweeps_per_source") for k, v in lg["variants"].items()},
+            "output_tt_equals_ours": {k: v.get("output_tt_equals_ours") for k, v in lg["variants"].items()},
+            "ours_ms_per_converged_source": tot["elapsed_ms"] / max(1, tot["sources"]),
+        }
+    except Exception:
+        pass
     if extras is not None:
         line["extras"] = extras
     if one_grid is not None:

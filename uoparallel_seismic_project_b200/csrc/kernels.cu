@@ -630,6 +630,46 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
   const bool multi = a.max_inner > 1;
   const int y = lane & 7;
   bool build_next = false;
+  int pend_tile = -1;        // finisher warp, one grid over several devices: tile whose cross-device wake-ups are still to be sent
+  unsigned pend_tmin = 0u;
+  // A changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected; the tile itself only
+  // needs another visit if its last in-tile pass still changed something.  `which`: 0 = every neighbour, 1 = only
+  // those owned by this part, 2 = only those owned by other parts.
+  auto wake = [&](int wtile, unsigned wtmin, bool wself, int which) {
+    const int ws = wtile / ntiles;
+    int wp = wtile - ws * ntiles;
+    const int wtz = wp % a.g.ntz; wp /= a.g.ntz;
+    const int wty = wp % a.g.nty;
+    const int wtx = wp / a.g.nty;
+    for (int m = lane; m < NMARK; m += 32) {
+      const int dx = m / 9 - XREACH, dy = (m / 3) % 3 - 1, dz = m % 3 - 1;
+      const int ux = wtx + dx, uy = wty + dy, uz = wtz + dz;
+      const bool self = (dx == 0 && dy == 0 && dz == 0);
+      bool reach = (abs(dx) - 1) * TX < RXY;  // x distance between the closest nodes of the two tiles
+      if (self && !wself) reach = false;
+      if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
+        const size_t u = (size_t)ws * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
+        unsigned* keyp = a.key;
+        const unsigned* tmaxp = a.tmax;
+        if constexpr (!PERSIST) {
+          if (a.nparts > 1) {  // the neighbour's x block may belong to another device: its owner keeps its key
+            const int o = (ux / a.tiles_per_block) % a.nparts;
+            if ((which == 1 && o != a.part) || (which == 2 && o == a.part)) continue;
+            keyp = a.part_key[o];
+            tmaxp = a.part_tmax[o];
+          }
+        }
+        // Downwind filter: every candidate that one of our lowered nodes can offer is
+        // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
+        // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
+        // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
+        bool useful = true;
+        if (tmaxp != nullptr && !self)
+          useful = __float_as_uint(__fadd_rn(__uint_as_float(wtmin), a.dmin)) < __ldcg(&tmaxp[u]);
+        if (useful) atomicMin(&keyp[u], wtmin);
+      }
+    }
+  };
   for (uint32_t it = 0;; ++it) {
     const int q = it & 1;
     mbar_wait(&full[q], (it >> 1) & 1);
@@ -707,7 +747,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     const int P = NW / nlive;
     const int unit = wq / P, part = wq - unit * P;
     const int xc = tx == 0 ? 1 : (tx == a.g.ntx - 1 ? 2 : 0);  // tile position along x: which columns can reach the grid at all
-    int f0 = ((xc * 6 + (PERSIST ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
+    // (the finisher of a multi-device part issues system-wide fences like the single-launch kernel's: same head starts)
+    int f0 = ((xc * 6 + ((PERSIST || a.nparts > 1) ? 3 : 0) + (nlive == 1 ? 0 : 1 + unit)) * MAX_PATTERNS) * MAX_WARPS + part;  // c_pdesc index, group 0
     // keep the index in ONE register: left alone, ptxas re-derives it (unit / part / table selects, 9 instructions)
     // in front of every one of the 18 pattern blocks of every tile
 #ifndef SWEEPTT_NO_PIN
@@ -901,39 +942,32 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
       s_tmin = 0x7f800000u;
       s_tmax = 0u;
     }
+    if constexpr (!PERSIST) {
+      // One grid over several devices: the wake-ups that cross to ANOTHER device need the tile's stores to be visible
+      // system-wide first.  They are sent one tile LATE, from here: by now the previous tile's stores have long
+      // drained, so the fence does not wait (issued right behind the stores it cost the finisher warp -- and with it
+      // the whole tile -- microseconds).  Wake-ups are only consumed after this launch, so the delay costs nothing.
+      if (a.nparts > 1 && pend_tile >= 0) {
+        __threadfence_system();
+        wake(pend_tile, pend_tmin, false, 2);
+        pend_tile = -1;
+      }
+    }
     if (any) {
       // single launch: the owners' stores (ordered before this point by the owners' barrier) must be visible
       // device-wide before any neighbour is woken up
-      if constexpr (PERSIST) __threadfence();
-      else if (a.nparts > 1) __threadfence_system();  // ... system-wide before the owner of a neighbour tile on ANOTHER device is
-      // a changed node reaches R <= 7 cells: every neighbour tile within that reach may be affected;
-      // the tile itself only needs another visit if its last in-tile pass still changed something
-      for (int m = lane; m < NMARK; m += 32) {
-        const int dx = m / 9 - XREACH, dy = (m / 3) % 3 - 1, dz = m % 3 - 1;
-        const int ux = tx + dx, uy = ty + dy, uz = tz + dz;
-        const bool self = (dx == 0 && dy == 0 && dz == 0);
-        bool reach = (abs(dx) - 1) * TX < RXY;  // x distance between the closest nodes of the two tiles
-        if (self && !last_pass_changed) reach = false;
-        if (reach && ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz) {
-          const size_t u = (size_t)s * ntiles + ((size_t)ux * a.g.nty + uy) * a.g.ntz + uz;
-          unsigned* keyp = a.key;
-          const unsigned* tmaxp = a.tmax;
-          if constexpr (!PERSIST) {
-            if (a.nparts > 1) {  // the neighbour's x block may belong to another device: its owner keeps its key
-              const int o = (ux / a.tiles_per_block) % a.nparts;
-              keyp = a.part_key[o];
-              tmaxp = a.part_tmax[o];
-            }
-          }
-          // Downwind filter: every candidate that one of our lowered nodes can offer is
-          // fl(delay + tt) >= fl(dmin + tmin) (rounding is monotone, delays >= dmin >= 0); a neighbour
-          // tile whose nodes are ALL already <= that bound cannot be improved by this change, so it is
-          // not woken up.  tmax[] is an upper bound of the tile's current maximum (values only fall).
-          bool useful = true;
-          if (tmaxp != nullptr && !self)
-            useful = __float_as_uint(__fadd_rn(__uint_as_float(tile_tmin), a.dmin)) < __ldcg(&tmaxp[u]);
-          if (useful) atomicMin(&keyp[u], tile_tmin);
+      if constexpr (PERSIST) {
+        __threadfence();
+        wake(tile, tile_tmin, last_pass_changed != 0, 0);
+      } else if (a.nparts > 1) {
+        wake(tile, tile_tmin, last_pass_changed != 0, 1);  // neighbours on this device (consumed after the launch)
+        const int bx = tx % a.tiles_per_block;  // only tiles at the edge of an ownership block have neighbours elsewhere
+        if ((bx < XREACH && tx >= XREACH) || (bx >= a.tiles_per_block - XREACH && tx + XREACH < a.g.ntx)) {
+          pend_tile = tile;
+          pend_tmin = tile_tmin;
         }
+      } else {
+        wake(tile, tile_tmin, last_pass_changed != 0, 0);
       }
     }
     if (lane == 31) {
@@ -953,6 +987,12 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         if (any) __threadfence();  // the neighbours' keys are set before the count can reach zero
         atomicSub(&S->inflight, 1u);
       }
+    }
+  }
+  if constexpr (!PERSIST) {
+    if (pend_tile >= 0) {  // (finisher warp) the last tile's cross-device wake-ups
+      __threadfence_system();
+      wake(pend_tile, pend_tmin, false, 2);
     }
   }
 }
