@@ -60,6 +60,7 @@ struct SolveState {
   unsigned long long units_changed;  // ... of which lowered at least one travel time
   int max_rounds;            // 0 = unlimited; the graph WHILE loop stops here
   unsigned kmin_bits;        // smallest activation key among dirty tiles (scan pass of the compaction)
+  unsigned ticket2;          // last-block-done ticket of scan_min_key (one grid over several devices)
   unsigned kmin_pub;         // one grid over several devices: smallest pending key at this part's last compaction
                              // (INF: nothing pending); read by the other parts and by the host's termination test
   // ---- single-launch (persistent) scheduling: work lists come in GENERATIONS built on the device ----

@@ -594,9 +594,14 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     DBG_BOUNDS(tz * TZ + AZ - ZHALO >= 0 && tz * TZ + AZ - ZHALO + SZD <= a.g.pz);
     DBG_BOUNDS(ty * TY + AY - RXY >= 0 && ty * TY + AY - RXY + D::SYD <= a.g.py);
     DBG_BOUNDS(tx * TX + AX - RXY >= 0 && tx * TX + AX - RXY + D::SXD <= a.g.px);
+    DBG_BOUNDS(a.slow_pb == 0 || (tx % a.tiles_per_block) * TX + (AX - RXY) + D::SXD <= a.slow_pb);
     // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
     mbar_expect_tx(&full[q], 2u * sizeof(float) * D::BOX_FLOATS);
-    tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY);
+    int cx = tx * TX + AX - RXY;
+    // one grid over several devices: the (read-only) slowness is kept LOCAL -- every owned x block with its own halo
+    // planes, slow_pb planes per block, in the order of the part's blocks -- so only travel times cross NVLink
+    if (a.slow_pb) cx = ((tx / a.tiles_per_block) / max(1, a.nparts)) * a.slow_pb + (tx % a.tiles_per_block) * TX + (AX - RXY);
+    tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, cx);
     tma_load_4d(sv + D::BOX_STRIDE, &tm_tt, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY, s);
   };
   // synchronous pop (prologue, and after a generation switch): next tile id or a marker; thread 0 only
@@ -656,7 +661,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
             const int o = (ux / a.tiles_per_block) % a.nparts;
             if ((which == 1 && o != a.part) || (which == 2 && o == a.part)) continue;
             keyp = a.part_key[o];
-            tmaxp = a.part_tmax[o];
+            tmaxp = a.part_tmax[o];  // (peer memory for a neighbour elsewhere; measured: dropping the filter there to save the
+                                     //  NVLink round trip wakes 4.6 % more tiles and gains nothing)
           }
         }
         // Downwind filter: every candidate that one of our lowered nodes can offer is
@@ -1007,6 +1013,29 @@ __global__ void __launch_bounds__(256) scan_min_key(const RelaxArgs a) {
     m = min(m, a.key[i]);
   m = __reduce_min_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(&a.st->kmin_bits, m);
+  if (a.nparts > 1) {
+    // One grid over several devices: the LAST block publishes this part's smallest pending key and resolves the
+    // threshold base once (the smallest key on ANY device -- a stale peer value is older, hence lower: only ever too
+    // careful -- but at most front_slack behind our own), so that select_tiles reads one local word instead of
+    // every block reading every peer over NVLink.
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&a.st->ticket2, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      __threadfence();
+      SolveState* S = a.st;
+      S->ticket2 = 0;
+      const unsigned own = atomicMin(&S->kmin_bits, 0x7f800000u);  // (read through L2)
+      unsigned g = own;
+      st_volatile_u32(a.part_kmin[a.part], own);
+      for (int q = 0; q < a.nparts; ++q)
+        if (q != a.part) g = min(g, ld_volatile_u32(a.part_kmin[q]));
+      if (own != 0x7f800000u) g = max(g, __float_as_uint(fmaxf(0.f, __uint_as_float(own) - a.front_slack)));
+      S->kmin_bits = g;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) select_tiles(const RelaxArgs a, unsigned long long cond) {
@@ -1017,14 +1046,7 @@ __global__ void __launch_bounds__(256) select_tiles(const RelaxArgs a, unsigned 
   // bucket: keys within `bucket` of the smallest pending key (Dijkstra-like ordering at tile
   // granularity; travel times below the bucket are final, so their tiles are not re-relaxed with
   // inputs that are still going to change)
-  unsigned kmin_bits = S->kmin_bits;
-  if (a.nparts > 1) {
-    // one grid over several devices: publish our smallest pending key and follow the smallest one anywhere (a stale
-    // peer value is older, hence lower: the threshold is only ever too careful)
-    if (blockIdx.x == 0 && threadIdx.x == 0) st_volatile_u32(a.part_kmin[a.part], kmin_bits);
-    for (int q = 0; q < a.nparts; ++q)
-      if (q != a.part) kmin_bits = min(kmin_bits, ld_volatile_u32(a.part_kmin[q]));
-  }
+  const unsigned kmin_bits = S->kmin_bits;  // (one grid over several devices: already the global front, see scan_min_key)
   const float kmin = __uint_as_float(kmin_bits);
   const unsigned thr = (a.bucket < 0.f) ? 0x7f7fffffu : __float_as_uint(kmin + a.bucket);
   const unsigned k = (i < total) ? a.key[i] : 0x7f800000u;
@@ -1419,9 +1441,11 @@ __global__ void __launch_bounds__(1024) compact_fused(const RelaxArgs a, unsigne
   if (a.nparts > 1) {  // (see select_tiles)
     if (threadIdx.x == 0) {
       unsigned g = s_min;
+      const unsigned own = g;
       st_volatile_u32(a.part_kmin[a.part], g);
       for (int q = 0; q < a.nparts; ++q)
         if (q != a.part) g = min(g, ld_volatile_u32(a.part_kmin[q]));
+      if (own != 0x7f800000u) g = max(g, __float_as_uint(fmaxf(0.f, __uint_as_float(own) - a.front_slack)));
       s_min = g;
     }
     __syncthreads();

@@ -61,10 +61,13 @@ struct RelaxArgs {
   int nparts;                  // 0 or 1: a single context
   int part;                    // index of this context
   int tiles_per_block;         // x tiles per ownership block: owner(tx) = (tx / tiles_per_block) % nparts
+  int slow_pb;                 // != 0: `slow` / the slowness tensor map hold this part's blocks only, each with its halo
+                               // planes: slow_pb = tiles_per_block * TX + 2 * 7 planes per block, blocks in ascending order
   unsigned* part_key[MAX_PARTS];    // every part's activation keys (peer memory)
   unsigned* part_tmax[MAX_PARTS];   // every part's per-tile upper bounds (peer memory; nullptr = no filter)
   unsigned* part_kmin[MAX_PARTS];   // every part's published smallest pending key: the activation bucket follows
-                                    // the smallest key on ANY device, so no device runs ahead of the front
+                                    // the smallest key on ANY device, so no device runs far ahead of the front
+  float front_slack;                // ... by more than this (travel-time units; a multiple of the bucket)
   int npat;                    // pattern groups (generic kernel; the stock kernels know theirs at compile time)
   int pat_begin[MAX_PATTERNS + 1];  // stock-star kernels: columns [pat_begin[p], pat_begin[p+1]) share pattern p
 };

@@ -218,7 +218,9 @@ struct sweeptt_ctx {
   int max_inner = 1;                   // in-tile passes per tile visit
   int force_window_axis = -1;          // forced caller axis of the kernel's register-window (z) axis
   int force_x_axis = -1;               // one grid over several devices: caller axis that becomes kernel x (block axis)
-  bool external_boxes = false;         // d_slow / d_tt belong to a SharedBox (one grid over several devices)
+  bool external_boxes = false;         // d_tt belongs to a SharedBox (one grid over several devices); d_slow is ours
+  int slow_pb = 0;                     // one grid over several devices: planes per block of the local slowness copy
+  long long slow_planes = 0;           // ... and its total number of planes
   // one grid over several devices (see RelaxArgs): this context's part of the job
   int mp_nparts = 0, mp_part = 0, mp_tiles_per_block = 1;
   unsigned* mp_key[MAX_PARTS] = {};
@@ -345,7 +347,8 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   cudaFree(c->d_out_ring);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
-  if (!c->external_boxes) { cudaFree(c->d_slow); cudaFree(c->d_tt); }
+  cudaFree(c->d_slow);
+  if (!c->external_boxes) cudaFree(c->d_tt);
   cudaFree(c->d_src); cudaFree(c->d_state);
   cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_keysnap); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
   cudaFree(c->d_stage); cudaFree(c->d_star);
@@ -781,7 +784,7 @@ static int build_maps(sweeptt_ctx* c) {
   int sxd, syd, szd;
   tiled_variant_dims(c->tl.rxy, &sxd, &syd, &szd);
   {
-    cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)g.px};
+    cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.py, (cuuint64_t)(c->slow_pb ? c->slow_planes : g.px)};
     cuuint64_t strides[2] = {(cuuint64_t)g.pz * 4, (cuuint64_t)g.sx * 4};
     cuuint32_t box[3] = {(cuuint32_t)szd, (cuuint32_t)syd, (cuuint32_t)sxd};
     cuuint32_t es[3] = {1, 1, 1};
@@ -901,6 +904,11 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.neg_zero = -0.0f;
   a.max_inner = c->max_inner;
   a.nparts = c->mp_nparts; a.part = c->mp_part; a.tiles_per_block = std::max(1, c->mp_tiles_per_block);
+  a.slow_pb = c->slow_pb;
+  {
+    static const double slack = getenv("SWEEPTT_FRONT_SLACK") ? atof(getenv("SWEEPTT_FRONT_SLACK")) : 1.0;  // in buckets
+    a.front_slack = c->bucket > 0.f ? (float)(slack * c->bucket) : 0.f;
+  }
   static const bool own_front = getenv("SWEEPTT_NO_GLOBAL_KMIN") != nullptr;  // (experiment: every part follows its own front)
   for (int q = 0; q < MAX_PARTS; ++q) {
     a.part_key[q] = c->mp_key[q];
@@ -1824,7 +1832,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   if (G > n[axis]) return fail("more slabs (%d) than planes (%d) along the slab axis", G, n[axis]);
 
   std::vector<Part> parts(G);
-  SharedBox box_slow, box_tt;
+  SharedBox box_tt;
   std::vector<int> devices;
   for (int p = 0; p < G; ++p) {
     parts[p].device = p % ndev;
@@ -1835,7 +1843,6 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
       pt.lease.release();
       if (pt.ctx) { cudaSetDevice(pt.device); cudaStreamSynchronize(pt.ctx->stream); sweeptt_destroy(pt.ctx); pt.ctx = nullptr; }
     }
-    box_slow.destroy();
     box_tt.destroy();
   };
   // ---- peer access for the per-part arrays (keys, bounds, state); the shared boxes get theirs from cuMemSetAccess ----
@@ -1864,7 +1871,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     g = pt.ctx->g;
   }
   // ownership blocks along kernel x: a few tiles each, dealt round-robin (block-cyclic)
-  int tpb = std::max(1, std::min(4, g.ntx / (4 * G)));
+  int tpb = std::max(1, std::min(8, g.ntx / (4 * G)));  // (measured on 2 GPUs, 1201x1201x251: 2 tiles 316 ms, 4: 232, 8: 213, 16: 210)
   if (const char* e = getenv("SWEEPTT_BLOCK_TILES")) tpb = std::max(1, atoi(e));
   const int nblocks = (g.ntx + tpb - 1) / tpb;
   for (int b = 0; b < nblocks; ++b) {
@@ -1895,7 +1902,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     }
     cuts.push_back(total);
     for (int d : devices) { cudaSetDevice(d); cudaFree(0); }  // primary contexts exist before memory is placed
-    if (!box_slow.create(cuts, chunk_dev, devices) || !box_tt.create(cuts, chunk_dev, devices)) { cleanup(); return 0; }
+    if (!box_tt.create(cuts, chunk_dev, devices)) { cleanup(); return 0; }
   }
   int R = 0;
   for (int l = 0; l < starsize; ++l) R = std::max(R, std::abs(axis == 0 ? fs[l].i : axis == 1 ? fs[l].j : fs[l].k));
@@ -1907,8 +1914,8 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   PhaseBarrier bar(G);
   Quiescence quiet(G);
   const int K = o.rounds_per_poll > 0 ? o.rounds_per_poll : 4;
-  float* const d_slow = reinterpret_cast<float*>(box_slow.va);
   float* const d_tt = reinterpret_cast<float*>(box_tt.va);
+  const int PB = tpb * TX + 2 * RXY_MAX;  // planes per block of the local slowness copies (block + halo on both sides)
   const float INF = std::numeric_limits<float>::infinity();
   std::atomic<int> setup_failed{0};
   std::vector<long long> batches(G, 0), idle_batches(G, 0);
@@ -1924,42 +1931,52 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     if (e__ != cudaSuccess && pt.ok) { pt.ok = 0; pt.err = std::string(#call) + ": " + cudaGetErrorString(e__); setup_failed = 1; } \
   } while (0)
     PCK(cudaSetDevice(pt.device));
-    // phase 1: +INF into the pages this part's DEVICE holds (both boxes: apron and not-yet-uploaded nodes)
-    for (const SharedBox* sb : {&box_slow, &box_tt})
-      for (const auto& ch : sb->chunks) {
-        // chunks of one device are filled by the first part on that device
-        int first = -1;
-        for (int q = 0; q < G && first < 0; ++q) if (parts[q].device == ch.device) first = q;
-        if (first != p) continue;
-        PCK(launch_fill(reinterpret_cast<float*>(sb->va + ch.off), (long long)(ch.size / 4), INF, c->stream));
-      }
+    // phase 1: +INF into the pages of the shared travel-time box that this part's DEVICE holds, and into the part's
+    // local slowness copy (every owned block with its halo planes; apron and out-of-grid planes stay +INF)
+    for (const auto& ch : box_tt.chunks) {
+      int first = -1;  // chunks of one device are filled by the first part on that device
+      for (int q = 0; q < G && first < 0; ++q) if (parts[q].device == ch.device) first = q;
+      if (first != p) continue;
+      PCK(launch_fill(reinterpret_cast<float*>(box_tt.va + ch.off), (long long)(ch.size / 4), INF, c->stream));
+    }
+    c->slow_pb = PB;
+    c->slow_planes = (long long)std::max<size_t>(1, pt.blocks.size()) * PB;
+    if (pt.ok && !dev_alloc(c, (void**)&c->d_slow, (size_t)c->slow_planes * g.sx * 4)) bail("local slowness copy");
+    if (pt.ok) PCK(launch_fill(c->d_slow, c->slow_planes * g.sx, INF, c->stream));
     PCK(cudaStreamSynchronize(c->stream));
     bar.wait();
-    // phase 2: upload the owned blocks of the model (sub-box in caller order -> padded shared box)
-    c->d_slow = d_slow; c->d_tt = d_tt; c->tt_cap = 1;
+    // phase 2: upload the owned blocks of the model + halo planes (sub-box in caller order -> padded local copy)
+    c->d_tt = d_tt; c->tt_cap = 1;
     c->have_model = true;
     if (pt.ok && !setup_failed) {
+      auto ext = [&](const std::pair<int, int>& b) {  // planes the block reads: itself + the star radius on both sides
+        return std::make_pair(std::max(0, b.first - RXY_MAX), std::min(g.nx, b.second + RXY_MAX));
+      };
       size_t stage_floats = 0;
       for (auto& b : pt.blocks) {
         int sub[3] = {nx, ny, nz};
-        sub[axis] = b.second - b.first;
+        sub[axis] = ext(b).second - ext(b).first;
         stage_floats = std::max(stage_floats, (size_t)sub[0] * sub[1] * sub[2]);
       }
       float* h_stage = nullptr;
       if (stage_floats && (!ensure_stage(c, stage_floats) || cudaMallocHost(&h_stage, stage_floats * 4) != cudaSuccess)) bail("staging");
-      for (auto& b : pt.blocks) {
+      for (size_t lb = 0; lb < pt.blocks.size(); ++lb) {
         if (!pt.ok) break;
+        const auto b = pt.blocks[lb];
+        const auto e = ext(b);
         int sub[3] = {nx, ny, nz}, org[3] = {0, 0, 0};
-        sub[axis] = b.second - b.first;
-        org[axis] = b.first;
+        sub[axis] = e.second - e.first;
+        org[axis] = e.first;
         const size_t cnt = (size_t)sub[0] * sub[1] * sub[2];
         if (!fetch(org, sub, h_stage)) { bail("reading the model"); break; }
         PCK(cudaMemcpyAsync(c->d_stage, h_stage, cnt * 4, cudaMemcpyHostToDevice, c->stream));
         BoxGeom gs = g;
-        gs.nx = b.second - b.first;
+        gs.nx = e.second - e.first;
         const long long ds[3] = {(long long)sub[1] * sub[2], (long long)sub[2], 1};
         for (int q = 0; q < 3; ++q) gs.dstride[q] = ds[g.perm[q]];
-        PCK(launch_pad_box(c->d_stage, d_slow + (size_t)b.first * g.sx, gs, c->stream));
+        // local plane of logical plane x of this block: lb * PB + (x - b.first) + 7  (= padded plane x + AX of the
+        // global box, shifted to the block's origin); launch_pad_box writes relative plane r at r + AX
+        PCK(launch_pad_box(c->d_stage, c->d_slow + ((long long)lb * PB + (e.first - b.first) + RXY_MAX - AX) * g.sx, gs, c->stream));
         unsigned r[6] = {0, 0, 0, 0, 0, 0};
         PCK(launch_min_slowness(c->d_stage, (long long)cnt, reinterpret_cast<unsigned*>(c->d_viol), c->stream));
         PCK(cudaMemcpyAsync(r, c->d_viol, sizeof r, cudaMemcpyDeviceToHost, c->stream));
