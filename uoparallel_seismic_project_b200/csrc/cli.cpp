@@ -92,7 +92,8 @@ int main(int argc, char* argv[]) {
   std::vector<char> pinned(numstart, 0);
   for (int s = 0; s < numstart; ++s) {
     // boxalloc (include/floatbox.h:122-123) -- page-locked when possible, so the copies back overlap the solve
-    tt[s] = static_cast<float*>(sweeptt_host_alloc(vol * sizeof(float)));
+    // (page-locking costs ~1 s per GB on the test box: worth it for a few boxes, not for config 3's 1.3 GB)
+    tt[s] = (vol * sizeof(float) * (size_t)numstart <= (size_t(512) << 20)) ? static_cast<float*>(sweeptt_host_alloc(vol * sizeof(float))) : nullptr;
     pinned[s] = tt[s] != nullptr;
     if (!tt[s]) tt[s] = static_cast<float*>(std::malloc(vol * sizeof(float)));
     if (!tt[s]) {

@@ -1083,13 +1083,26 @@ static int build_plan(sweeptt_ctx* c) {
   want_groups = std::max(1, std::min(want_groups, MAX_GROUPS));
   // Persistent waves may run K at a time, each on 1/K of the SMs (its own stream): a wave's start and end expose
   // fewer ready tiles than there are SMs (the front is small), and the time lost there shrinks with the SMs per wave.
-  int kstreams = 1;
+  int kstreams = 2;  // (measured on config 3, 111 sources: 1 stream 345.6 ms, 2 streams 338.2 ms, 4 streams 381.7 ms)
   if (const char* e = getenv("SWEEPTT_WAVE_STREAMS")) kstreams = std::max(1, std::min(atoi(e), MAX_GROUPS));
   const int nwaves_total = (c->nsrc + wave_size - 1) / wave_size;
   if (!persistent || nwaves_total < 2 * kstreams) kstreams = 1;
+  if (c->opts.profile_kernels) kstreams = 1;  // per-launch event timing: one launch at a time, on the whole device
+  // Wave sizes.  Persistent waves of 4 or more sources run at the same rate (measured: 4 sources 0.549 of the roof,
+  // 8: 0.549, 7+7: 0.556; ONE source 0.49), and the device->host copies of the LAST wave cannot hide behind any
+  // solve, so the last wave is kept small (4 sources) and the others share the rest evenly.
+  std::vector<int> sizes;
+  if (persistent && c->nsrc > wave_size && c->nsrc >= 8 && !getenv("SWEEPTT_WAVE")) {
+    const int rest = c->nsrc - 4;
+    const int nw = (rest + wave_size - 1) / wave_size;
+    for (int w = 0; w < nw; ++w) sizes.push_back((int)((long long)rest * (w + 1) / nw - (long long)rest * w / nw));
+    sizes.push_back(4);
+  } else {
+    for (int s0 = 0; s0 < c->nsrc; s0 += wave_size) sizes.push_back(std::min(wave_size, c->nsrc - s0));
+  }
   int slot = 1, wave = 0;
-  for (int s0 = 0; s0 < c->nsrc; s0 += wave_size, ++wave) {
-    const int ns = std::min(wave_size, c->nsrc - s0);
+  for (int s0 = 0; wave < (int)sizes.size(); s0 += sizes[wave], ++wave) {
+    const int ns = sizes[wave];
     const int parts = persistent ? 1 : std::min(want_groups, ns);
     for (int g = 0; g < parts; ++g) {
       sweeptt_ctx::Slice sl;
@@ -1529,6 +1542,12 @@ static int ensure_out_ring(sweeptt_ctx* c, size_t dense_floats, int want_boxes) 
 static int solve_on_device(int device, const sweeptt_opts& o, const float* slowness, int nx, int ny, int nz,
                            const FS* fs, int starsize, const START* starts, int numstart, float* const* tt_out,
                            sweeptt_stats* st) {
+  static const bool timing = getenv("SWEEPTT_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (timing) fprintf(stderr, "[sweeptt-timing] dev %d %-12s +%.3f ms\n", device, what,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   CachedCtx cc(device, o);  // (exclusive use of the device's cached context for this call)
   sweeptt_ctx* c = cc.ctx;
   if (!c) return 0;
@@ -1540,12 +1559,15 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
   CK(cudaEventSynchronize(c->ev3));
   float h2d_ms = 0;  // read now: the run below reuses these events
   CK(cudaEventElapsedTime(&h2d_ms, c->ev2, c->ev3));
+  lap("set_model");
   const bool same_star = c->have_star && (int)c->fs.size() == starsize &&
                          std::memcmp(c->fs.data(), fs, sizeof(FS) * starsize) == 0;
   if (!same_star && !sweeptt_set_star(c, fs, starsize)) return 0;
   if (!sweeptt_set_sources(c, starts, numstart)) return 0;
+  lap("star+sources");
   ConstLease lease;
   if (!ready(c, &lease)) return 0;
+  lap("ready");
   // device -> host, overlapped with the solve of the later waves: un-pad into a ring of dense boxes on the solve
   // stream, one contiguous copy per source on the copy stream
   const size_t dense = (size_t)nx * ny * nz;
@@ -1568,8 +1590,10 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
     return 1;
   };
   if (!run_locked(c, st, drain)) return 0;
+  lap("solved");
   const auto t_solved = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(c->copy_stream));
+  lap("copied");
   st->h2d_ms = h2d_ms;
   st->h2d_bytes = (long long)nx * ny * nz * 4;
   // what the copies cost on top of the solve: the tail after the last wave converged (the rest ran behind it)
