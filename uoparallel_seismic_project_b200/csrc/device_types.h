@@ -21,7 +21,11 @@ constexpr int ZHALO = 8;                 // z halo staged on both sides (16-byte
 constexpr int SZD = TZ + 2 * ZHALO + 4;  // smem/TMA row length: 28 floats; 28/4 = 7 is odd,
                                          // which makes the quarter-warp LDS.128 conflict-free
 constexpr int WIN = KZ + 2 * ZHALO;      // 24-float register window per (i,j) column
-constexpr int MAX_WARPS = 16;            // compute warps per CTA (one more warp feeds the TMA pipeline)
+#ifndef SWEEPTT_NW
+#define SWEEPTT_NW 16
+#endif
+constexpr int MAX_WARPS = SWEEPTT_NW;    // compute warps per CTA of the 5-FS / 818-FS kernels (even; 20 = five per scheduler
+                                         // needs <= 102 registers per thread)
 constexpr int XREACH = (7 + TX - 1) / TX;  // tiles that a changed node (reach <= 7 nodes) can affect along x
 constexpr int NMARK = (2 * XREACH + 1) * 9;
 
@@ -99,7 +103,7 @@ struct StarDev {   // star as the simple kernel / verifier read it (global memor
 constexpr int MAX_PARTS = 16;    // devices (or contexts sharing devices) that one grid can be spread over
 
 constexpr int MAX_COLUMNS = 320;
-constexpr int MAX_PATTERNS = 31;
+constexpr int MAX_PATTERNS = SWEEPTT_NW > 20 ? 20 : SWEEPTT_NW > 16 ? 24 : 31;  // (the column tables must fit 64 KB of constant memory)
 constexpr int MAX_COL_HD = 4096;
 constexpr int MAX_EXTRA = 128;
 constexpr int NXCLASS = 3;       // column tables per tile position along x: interior, first tile, last tile (kernels.cu c_pdesc)
