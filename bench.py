@@ -308,7 +308,7 @@ def timed_resident(P, torch, ctx, stream, flush, steps, warmup, barrier, before_
         before_timed()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    acc = dict(relaxations=0, launches=0, rounds=0, tiles=0, relax_launches=0)
+    acc = dict(relaxations=0, launches=0, rounds=0, tiles=0, relax_launches=0, units=0)
     wall0 = time.perf_counter()
     for k in range(steps):
         flush.zero_()                      # L2 flush between timed iterations (not timed)
@@ -316,7 +316,7 @@ def timed_resident(P, torch, ctx, stream, flush, steps, warmup, barrier, before_
         st = ctx.run()
         ev[k][1].record(stream)
         acc["relaxations"] += st.relaxations; acc["launches"] += st.kernel_launches; acc["rounds"] += st.rounds
-        acc["tiles"] += st.tile_visits; acc["relax_launches"] += st.relax_launches
+        acc["tiles"] += st.tile_visits; acc["relax_launches"] += st.relax_launches; acc["units"] += st.units_run
     barrier()
     acc["wall_ms"] = (time.perf_counter() - wall0) * 1e3
     acc["dev_ms"] = sum(a.elapsed_time(b) for a, b in ev)
@@ -580,6 +580,10 @@ def run_ours(args):
             "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_achieved / hbm_peak if hbm_achieved else None,
                     "note": "12 B per node per tile visit; the path is ~50x away from the HBM roof (SURVEY.md 8d)"},
+            # executed but not counted: lanes of partly filled edge tiles and pulls across the box boundary
+            # (241 = 30 tiles + 1 node along two axes): counted pulls / (unit visits x 256 nodes x 817 pull offsets)
+            "counted_over_executed_lane_pulls": acc["relaxations"] / max(1, acc["units"] * 256 * 817),
+            "frac_of_executed_lane_pulls": (roof["lane_ops"] / roof["peak_ops"]) / max(1e-9, acc["relaxations"] / max(1, acc["units"] * 256 * 817)),
             "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": alg_bytes_per_launch,
         },
