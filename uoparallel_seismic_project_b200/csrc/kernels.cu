@@ -594,13 +594,13 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
     DBG_BOUNDS(tz * TZ + AZ - ZHALO >= 0 && tz * TZ + AZ - ZHALO + SZD <= a.g.pz);
     DBG_BOUNDS(ty * TY + AY - RXY >= 0 && ty * TY + AY - RXY + D::SYD <= a.g.py);
     DBG_BOUNDS(tx * TX + AX - RXY >= 0 && tx * TX + AX - RXY + D::SXD <= a.g.px);
-    DBG_BOUNDS(a.slow_pb == 0 || (tx % a.tiles_per_block) * TX + (AX - RXY) + D::SXD <= a.slow_pb);
+    DBG_BOUNDS(a.slow_pb == 0 || (a.tx_owner[tx] == a.part && a.tx_slow0[tx] >= 0));
     // padded coords of the staged box origin: logical - (RXY, RXY, ZHALO) + apron
     mbar_expect_tx(&full[q], 2u * sizeof(float) * D::BOX_FLOATS);
     int cx = tx * TX + AX - RXY;
     // one grid over several devices: the (read-only) slowness is kept LOCAL -- every owned x block with its own halo
     // planes, slow_pb planes per block, in the order of the part's blocks -- so only travel times cross NVLink
-    if (a.slow_pb) cx = ((tx / a.tiles_per_block) / max(1, a.nparts)) * a.slow_pb + (tx % a.tiles_per_block) * TX + (AX - RXY);
+    if (a.slow_pb) cx = a.tx_slow0[tx] + (AX - RXY);
     tma_load_3d(sv, &tm_slow, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, cx);
     tma_load_4d(sv + D::BOX_STRIDE, &tm_tt, &full[q], tz * TZ + AZ - ZHALO, ty * TY + AY - RXY, tx * TX + AX - RXY, s);
   };
@@ -658,7 +658,7 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         const unsigned* tmaxp = a.tmax;
         if constexpr (!PERSIST) {
           if (a.nparts > 1) {  // the neighbour's x block may belong to another device: its owner keeps its key
-            const int o = (ux / a.tiles_per_block) % a.nparts;
+            const int o = a.tx_owner[ux];
             if ((which == 1 && o != a.part) || (which == 2 && o == a.part)) continue;
             keyp = a.part_key[o];
             tmaxp = a.part_tmax[o];  // (peer memory for a neighbour elsewhere; measured: dropping the filter there to save the
@@ -967,8 +967,8 @@ relax_tiled(const __grid_constant__ CUtensorMap tm_slow, const __grid_constant__
         wake(tile, tile_tmin, last_pass_changed != 0, 0);
       } else if (a.nparts > 1) {
         wake(tile, tile_tmin, last_pass_changed != 0, 1);  // neighbours on this device (consumed after the launch)
-        const int bx = tx % a.tiles_per_block;  // only tiles at the edge of an ownership block have neighbours elsewhere
-        if ((bx < XREACH && tx >= XREACH) || (bx >= a.tiles_per_block - XREACH && tx + XREACH < a.g.ntx)) {
+        // only tiles at the edge of an ownership block have neighbours elsewhere
+        if (a.tx_owner[max(tx - XREACH, 0)] != a.part || a.tx_owner[min(tx + XREACH, a.g.ntx - 1)] != a.part) {
           pend_tile = tile;
           pend_tmin = tile_tmin;
         }
@@ -1247,13 +1247,13 @@ __global__ void init_sources_kernel(const RelaxArgs a) {
   const int px = a.src_xyz[3 * s], py = a.src_xyz[3 * s + 1], pz = a.src_xyz[3 * s + 2];
   if (px < 0 || px >= a.g.nx || py < 0 || py >= a.g.ny || pz < 0 || pz >= a.g.nz) return;
   // (one grid over several devices: the owner of the start's x block writes the 0, every part lists its own tiles)
-  if (threadIdx.x == 63 && (a.nparts <= 1 || ((px / TX) / a.tiles_per_block) % a.nparts == a.part))
+  if (threadIdx.x == 63 && (a.nparts <= 1 || a.tx_owner[px / TX] == a.part))
     a.tt[(size_t)s * a.g.vol + ((size_t)(px + AX) * a.g.py + (py + AY)) * a.g.pz + (pz + AZ)] = 0.0f;
   if (threadIdx.x < NMARK) {
     const int tid = threadIdx.x;
     const int ux = px / TX + tid / 9 - XREACH, uy = py / TY + (tid / 3) % 3 - 1, uz = pz / TZ + tid % 3 - 1;
     if (ux >= 0 && ux < a.g.ntx && uy >= 0 && uy < a.g.nty && uz >= 0 && uz < a.g.ntz &&
-        (a.nparts <= 1 || (ux / a.tiles_per_block) % a.nparts == a.part)) {
+        (a.nparts <= 1 || a.tx_owner[ux] == a.part)) {
       const unsigned ntiles = a.g.ntx * a.g.nty * a.g.ntz;
       const unsigned pos = atomicAdd(&a.st->count[0], 1u);
       a.worklist[pos] = s * ntiles + (ux * a.g.nty + uy) * a.g.ntz + uz;

@@ -60,9 +60,10 @@ struct RelaxArgs {
   // peer memory with the same TMA loads and wakes the owner of a neighbour tile through that part's key array ----
   int nparts;                  // 0 or 1: a single context
   int part;                    // index of this context
-  int tiles_per_block;         // x tiles per ownership block: owner(tx) = (tx / tiles_per_block) % nparts
+  const unsigned char* tx_owner;    // [ntx] owner part of every tile column along x (blocks of a few tiles, dealt round-robin)
+  const int* tx_slow0;              // [ntx] owned tiles: first plane of the tile's staged box in this part's local slowness copy
   int slow_pb;                 // != 0: `slow` / the slowness tensor map hold this part's blocks only, each with its halo
-                               // planes: slow_pb = tiles_per_block * TX + 2 * 7 planes per block, blocks in ascending order
+                               // planes (slow_pb planes per block, blocks in ascending order)
   unsigned* part_key[MAX_PARTS];    // every part's activation keys (peer memory)
   unsigned* part_tmax[MAX_PARTS];   // every part's per-tile upper bounds (peer memory; nullptr = no filter)
   unsigned* part_kmin[MAX_PARTS];   // every part's published smallest pending key: the activation bucket follows

@@ -222,7 +222,9 @@ struct sweeptt_ctx {
   int slow_pb = 0;                     // one grid over several devices: planes per block of the local slowness copy
   long long slow_planes = 0;           // ... and its total number of planes
   // one grid over several devices (see RelaxArgs): this context's part of the job
-  int mp_nparts = 0, mp_part = 0, mp_tiles_per_block = 1;
+  int mp_nparts = 0, mp_part = 0;
+  unsigned char* d_tx_owner = nullptr;  // [ntx] owner of every tile column along x
+  int* d_tx_slow0 = nullptr;            // [ntx] first local slowness plane of every owned tile's staged box
   unsigned* mp_key[MAX_PARTS] = {};
   unsigned* mp_tmax[MAX_PARTS] = {};
   unsigned* mp_kmin[MAX_PARTS] = {};
@@ -348,6 +350,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow);
+  cudaFree(c->d_tx_owner); cudaFree(c->d_tx_slow0);
   if (!c->external_boxes) cudaFree(c->d_tt);
   cudaFree(c->d_src); cudaFree(c->d_state);
   cudaFree(c->d_worklist); cudaFree(c->d_key); cudaFree(c->d_tmax); cudaFree(c->d_busy); cudaFree(c->d_keysnap); cudaFree(c->d_tile_pulls); cudaFree(c->d_viol);
@@ -903,7 +906,8 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   a.nextra = (int)c->star.extra.size();
   a.neg_zero = -0.0f;
   a.max_inner = c->max_inner;
-  a.nparts = c->mp_nparts; a.part = c->mp_part; a.tiles_per_block = std::max(1, c->mp_tiles_per_block);
+  a.nparts = c->mp_nparts; a.part = c->mp_part;
+  a.tx_owner = c->d_tx_owner; a.tx_slow0 = c->d_tx_slow0;
   a.slow_pb = c->slow_pb;
   {
     static const double slack = getenv("SWEEPTT_FRONT_SLACK") ? atof(getenv("SWEEPTT_FRONT_SLACK")) : 1.0;  // in buckets
@@ -1894,13 +1898,22 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     if (!compute_geometry(pt.ctx, nx, ny, nz, &pt.ctx->g)) { cleanup(); return 0; }
     g = pt.ctx->g;
   }
-  // ownership blocks along kernel x: a few tiles each, dealt round-robin (block-cyclic)
-  int tpb = std::max(1, std::min(8, g.ntx / (4 * G)));  // (measured on 2 GPUs, 1201x1201x251: 2 tiles 316 ms, 4: 232, 8: 213, 16: 210)
-  if (const char* e = getenv("SWEEPTT_BLOCK_TILES")) tpb = std::max(1, atoi(e));
-  const int nblocks = (g.ntx + tpb - 1) / tpb;
+  // Ownership blocks along kernel x, dealt round-robin (block-cyclic): G * cycles blocks of (almost) equal size, about
+  // 8 tiles each (2 GPUs, 1201x1201x251: blocks of 2 tiles 267 ms, 4: 227, 8: 213, 16: 210), so that every part owns
+  // the same number of tiles to within `cycles`.
+  int tpb_target = 8;
+  if (const char* e = getenv("SWEEPTT_BLOCK_TILES")) tpb_target = std::max(1, atoi(e));
+  const int cycles = std::max(1, (g.ntx + G * tpb_target / 2) / (G * tpb_target));
+  const int nblocks = std::min(g.ntx, G * cycles);
+  std::vector<int> blk_start(nblocks + 1);
+  for (int b = 0; b <= nblocks; ++b) blk_start[b] = (int)((long long)g.ntx * b / nblocks);
+  int tpb = 1;  // largest block, in tiles
+  std::vector<unsigned char> tx_owner(g.ntx);
   for (int b = 0; b < nblocks; ++b) {
-    const int x0 = b * tpb * TX, x1 = std::min(g.nx, (b + 1) * tpb * TX);
+    tpb = std::max(tpb, blk_start[b + 1] - blk_start[b]);
+    const int x0 = blk_start[b] * TX, x1 = std::min(g.nx, blk_start[b + 1] * TX);
     if (x0 < x1) parts[b % G].blocks.push_back({x0, x1});
+    for (int t = blk_start[b]; t < blk_start[b + 1]; ++t) tx_owner[t] = (unsigned char)(b % G);
   }
   // memory chunks follow the blocks (rounded to the allocation granularity; a chunk may be empty on small grids)
   {
@@ -1920,7 +1933,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     std::vector<size_t> cuts;
     std::vector<int> chunk_dev;
     for (int b = 0; b < nblocks; ++b) {
-      const size_t first_plane = b == 0 ? 0 : (size_t)b * tpb * TX + AX;  // padded plane index where the block starts
+      const size_t first_plane = b == 0 ? 0 : (size_t)blk_start[b] * TX + AX;  // padded plane index where the block starts
       cuts.push_back(std::min(total, first_plane * plane_bytes / gran * gran));
       chunk_dev.push_back(parts[b % G].device);
     }
@@ -2030,7 +2043,20 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
     bar.wait();
     // phase 4: everybody's arrays exist -> exchange the pointers, take the constant tables, reset
     if (pt.ok && !setup_failed) {
-      c->mp_nparts = G; c->mp_part = p; c->mp_tiles_per_block = tpb;
+      c->mp_nparts = G; c->mp_part = p;
+      {
+        // per tile column: its owner, and (owned columns) where its staged box starts in the local slowness copy:
+        // block lb of this part starts at local plane lb * PB, logical plane x of the block at lb * PB + (x - x0) + 7
+        std::vector<int> slow0(g.ntx, -1);
+        for (size_t lb = 0; lb < pt.blocks.size(); ++lb)
+          for (int t = pt.blocks[lb].first / TX; t * TX < pt.blocks[lb].second; ++t) slow0[t] = (int)lb * PB + (t * TX - pt.blocks[lb].first);
+        if (cudaMalloc(&c->d_tx_owner, g.ntx) != cudaSuccess || cudaMalloc(&c->d_tx_slow0, sizeof(int) * g.ntx) != cudaSuccess ||
+            cudaMemcpy(c->d_tx_owner, tx_owner.data(), g.ntx, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(c->d_tx_slow0, slow0.data(), sizeof(int) * g.ntx, cudaMemcpyHostToDevice) != cudaSuccess) {
+          fail("per-column ownership tables: %s", cudaGetErrorString(cudaGetLastError()));
+          bail("tables");
+        }
+      }
       for (int q = 0; q < G; ++q) {
         c->mp_key[q] = parts[q].ctx->d_key;
         c->mp_tmax[q] = parts[q].ctx->d_tmax;
@@ -2144,7 +2170,7 @@ static int solve_slabs_impl(const std::function<int(const int*, const int*, floa
   total.h2d_bytes = (long long)nx * ny * nz * 4;
   total.d2h_bytes = (long long)nx * ny * nz * 4;
   if (o.verbose > 0) {
-    fprintf(stderr, "[sweeptt] one grid over %d parts (%zu devices), %d blocks of %d tiles: set-up %.1f ms, solve %.1f ms, gather %.1f ms; batches per part:",
+    fprintf(stderr, "[sweeptt] one grid over %d parts (%zu devices), %d blocks of <= %d tiles: set-up %.1f ms, solve %.1f ms, gather %.1f ms; batches per part:",
             G, devices.size(), nblocks, tpb, total.h2d_ms, total.solve_ms, total.d2h_ms);
     for (int p = 0; p < G; ++p) fprintf(stderr, " %lld (%lld without work, %.1f ms in batches with work, %lld tiles)", batches[p], idle_batches[p], busy_ms[p], (long long)parts[p].ctx->h_state->tile_visits);
     fprintf(stderr, "\n");
