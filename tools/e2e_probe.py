@@ -7,12 +7,15 @@ import numpy as np, torch
 import uoparallel_seismic_project_b200 as P
 from uoparallel_seismic_project_b200 import api, workloads as W
 nsrc = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+pageable = len(sys.argv) > 2 and sys.argv[2] == "pageable"
 dims = (241, 241, 51)
 v = W.heterogeneous_field(dims, 7)
 starts = W.starts(111)[:nsrc]
 star = P.make_star(W.star("818"))
 hv = torch.from_numpy(v).pin_memory()
-hout = torch.empty((nsrc,) + dims, dtype=torch.float32).pin_memory()
+hout = torch.empty((nsrc,) + dims, dtype=torch.float32)
+if not pageable:
+    hout = hout.pin_memory()
 st_arr = api._make_starts(starts)
 ptrs = (ctypes.c_void_p * nsrc)(*[hout[s].data_ptr() for s in range(nsrc)])
 opts = api._opts(device=0)

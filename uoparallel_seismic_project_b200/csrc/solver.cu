@@ -210,6 +210,7 @@ struct sweeptt_ctx {
   // stream and copied out by the copy stream while the next wave is being relaxed
   cudaStream_t copy_stream = nullptr;
   float* d_out_ring = nullptr;
+  float* h_out_ring = nullptr;  // page-locked twin of the ring: stop-over for results that go to PAGEABLE caller boxes
   size_t out_ring_boxes = 0, out_ring_box_floats = 0;
   std::vector<cudaEvent_t> ring_unpadded, ring_copied;
 
@@ -347,6 +348,7 @@ extern "C" void sweeptt_destroy(sweeptt_ctx* c) {
   for (auto e : c->ring_unpadded) cudaEventDestroy(e);
   for (auto e : c->ring_copied) cudaEventDestroy(e);
   cudaFree(c->d_out_ring);
+  if (c->h_out_ring) cudaFreeHost(c->h_out_ring);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaFree(c->d_slow);
@@ -1523,6 +1525,14 @@ extern "C" void sweeptt_release_cache(void) {
   }
 }
 
+namespace {
+struct HostCopy { void* dst; const void* src; size_t bytes; };
+void CUDART_CB host_copy_fn(void* p) {
+  const HostCopy* j = static_cast<const HostCopy*>(p);
+  std::memcpy(j->dst, j->src, j->bytes);
+}
+}  // namespace
+
 // Ring of dense staging boxes for the way out: box s is un-padded on the solve stream (a few microseconds of SM
 // time behind the wave that produced it) and copied to the host by the copy stream while the next wave is relaxed.
 static int ensure_out_ring(sweeptt_ctx* c, size_t dense_floats, int want_boxes) {
@@ -1531,6 +1541,7 @@ static int ensure_out_ring(sweeptt_ctx* c, size_t dense_floats, int want_boxes) 
   if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
   dev_free(c, c->d_out_ring, c->out_ring_boxes * c->out_ring_box_floats * 4);
   c->d_out_ring = nullptr; c->out_ring_boxes = 0; c->out_ring_box_floats = 0;
+  if (c->h_out_ring) { cudaFreeHost(c->h_out_ring); c->h_out_ring = nullptr; }
   if (!dev_alloc(c, (void**)&c->d_out_ring, boxes * dense_floats * 4)) return 0;
   c->out_ring_boxes = boxes; c->out_ring_box_floats = dense_floats;
   while (c->ring_unpadded.size() < boxes) {
@@ -1578,6 +1589,29 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
   if (!ensure_out_ring(c, dense, 2 * std::max(1, std::min(numstart, 16)))) return 0;
   size_t ring_pos = 0;
   std::vector<char> ring_used(c->out_ring_boxes, 0);
+  // page-locked or pageable destination?  (all boxes of a call are assumed to be of one kind: the first decides)
+  bool pageable_out = false;
+  {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, tt_out[0]) != cudaSuccess) { cudaGetLastError(); pageable_out = true; }
+    else pageable_out = pa.type == cudaMemoryTypeUnregistered;
+    if (getenv("SWEEPTT_NO_HOST_RING")) pageable_out = false;
+    if (pageable_out && !c->h_out_ring &&
+        cudaHostAlloc(&c->h_out_ring, c->out_ring_boxes * dense * 4, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      c->h_out_ring = nullptr;
+      pageable_out = false;  // no page-locked memory to be had: plain (staged) copies
+    }
+  }
+  std::vector<HostCopy*> jobs;
+  struct JobGuard {  // (an error return must not free a job whose callback is still queued)
+    std::vector<HostCopy*>& j;
+    cudaStream_t* st;
+    ~JobGuard() {
+      if (!j.empty() && *st) cudaStreamSynchronize(*st);
+      for (auto* x : j) delete x;
+    }
+  } job_guard{jobs, &c->copy_stream};
   const auto t_first = std::chrono::steady_clock::now();
   auto drain = [&](int s0, int ns, cudaStream_t st) -> int {
     for (int s = s0; s < s0 + ns; ++s) {
@@ -1587,7 +1621,17 @@ static int solve_on_device(int device, const sweeptt_opts& o, const float* slown
       CK(launch_unpad_box(c->d_tt + (size_t)s * c->g.vol, box, c->g, st));
       CK(cudaEventRecord(c->ring_unpadded[slot], st));
       CK(cudaStreamWaitEvent(c->copy_stream, c->ring_unpadded[slot], 0));
-      CK(cudaMemcpyAsync(tt_out[s], box, dense * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (pageable_out) {
+        // the caller's box is plain malloc memory (the reference's boxalloc): a device->pageable copy would block this
+        // thread -- and with it the enqueueing of the next waves -- at the driver's staging speed.  Stop over in the
+        // page-locked twin of the ring and let the copy stream's host callback do the memcpy behind the solve.
+        float* hbox = c->h_out_ring + slot * dense;
+        CK(cudaMemcpyAsync(hbox, box, dense * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        jobs.push_back(new HostCopy{tt_out[s], hbox, dense * 4});
+        CK(cudaLaunchHostFunc(c->copy_stream, host_copy_fn, jobs.back()));
+      } else {
+        CK(cudaMemcpyAsync(tt_out[s], box, dense * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+      }
       CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
       ring_used[slot] = 1;
     }
