@@ -21,6 +21,7 @@ import ctypes
 import hashlib
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -273,13 +274,20 @@ def run_reference(args):
     return 0
 
 
+def kernel_code_sha256():
+    """sha256 of csrc/kernels.cu with comments and white space removed (a comment edit does not stale the capture)."""
+    src = (ROOT / "uoparallel_seismic_project_b200" / "csrc" / "kernels.cu").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    return hashlib.sha256("".join(src.split()).encode()).hexdigest()
+
+
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture -- only while csrc/kernels.cu is still the file that was profiled (else the number is stale: None)."""
+    capture -- only while csrc/kernels.cu is still the code that was profiled (else the number is stale: None)."""
     try:
         t = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
-        sha = hashlib.sha256((ROOT / "uoparallel_seismic_project_b200" / "csrc" / "kernels.cu").read_bytes()).hexdigest()
-        if t.get("kernels_cu_sha256") != sha:
+        if t.get("kernels_cu_code_sha256") != kernel_code_sha256():
             return None, f"stale: {t.get('source')} was taken with another kernels.cu"
         return t["dram_bytes_per_launch"], t["source"]
     except Exception:

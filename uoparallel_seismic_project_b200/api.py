@@ -263,10 +263,11 @@ def solve(slowness, star, starts, *, delta: float = 10.0, out=None, device: int 
 
 def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, delta: float = 10.0,
                 max_rounds: int | None = None, rounds_per_poll: int | None = None, verbose: int | None = None):
-    """ONE source on ONE grid decomposed into `num_slabs` 1-D slabs over the visible GPUs (slabs share
-    devices round-robin when there are more slabs than GPUs), halo planes min-merged over NVLink
-    peer access after every local convergence.  Replaces the MPI ghost-cell programs
-    (mpi/16partsmpi.c:740-909).  Returns (tt float32[nx,ny,nz], SweepStats)."""
+    """ONE source on ONE grid spread over `num_slabs` parts (the visible GPUs; more parts than GPUs share devices
+    round-robin): the travel-time box is one range of peer memory whose pages are dealt block-cyclically along
+    `slab_axis`, every part relaxes its own blocks and reads halo planes from the owner over NVLink inside the
+    relaxation kernel -- no exchange step.  Replaces the MPI ghost-cell programs (mpi/16partsmpi.c:740-909).
+    Returns (tt float32[nx,ny,nz], SweepStats)."""
     lib = load_library()
     v = np.ascontiguousarray(slowness, dtype=np.float32)
     nx, ny, nz = v.shape
@@ -282,7 +283,7 @@ def solve_slabs(slowness, star, start, *, num_slabs: int, slab_axis: int = 0, de
 
 
 def solve_slabs_vbox(path, star, start, *, num_slabs: int, slab_axis: int = 0, delta: float = 10.0):
-    """Like solve_slabs, but every slab reads only its planes from the .vbox file (subset loader)."""
+    """Like solve_slabs, but every part reads only the planes of its blocks from the .vbox file (subset loader)."""
     lib = load_library()
     d = (C.c_int * 3)()
     _check(lib.sweeptt_vbox_dims(os.fsencode(path), d), "sweeptt_vbox_dims")

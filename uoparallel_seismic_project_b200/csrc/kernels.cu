@@ -27,8 +27,11 @@
 //                     verification path and the fallback for stars wider than the halo.
 //   count_violations  the fixed-point invariant (testconvergence,
 //                     old/wavefront-openmp/wave-multistart.c:300-347) on the device.
-//   fill/pad/unpad/init_sources/min_slowness/merge_halo  the device float-box pool's utilities
-//                     (boxsetall/boxput, include/floatbox.h:176-199) and the slab halo min-merge.
+//   fill/pad/unpad/init_sources/min_slowness  the device float-box pool's utilities
+//                     (boxsetall/boxput, include/floatbox.h:176-199).
+// One grid over several devices (solver.cu, sweeptt_solve_slabs) runs relax_tiled unchanged on a travel-time box
+// whose pages live block-cyclically on the devices: halo planes arrive over NVLink through the same TMA loads,
+// neighbours on other devices are woken through their owner's key array (RelaxArgs::part_key, tx_owner).
 #include "kernels.h"
 
 #include <cuda_runtime.h>

@@ -215,7 +215,7 @@ struct sweeptt_ctx {
   std::vector<cudaEvent_t> ring_unpadded, ring_copied;
 
   std::vector<cudaEvent_t> prof_events;
-  bool allow_outside_sources = false;  // slab contexts: the start may lie in another slab
+  bool allow_outside_sources = false;  // (internal) accept start points outside the model
   int max_inner = 1;                   // in-tile passes per tile visit
   int force_window_axis = -1;          // forced caller axis of the kernel's register-window (z) axis
   int force_x_axis = -1;               // one grid over several devices: caller axis that becomes kernel x (block axis)
@@ -924,7 +924,8 @@ static RelaxArgs make_args(sweeptt_ctx* c) {
   for (size_t i = 0; i < c->pat_begin.size() && i <= (size_t)MAX_PATTERNS; ++i) a.pat_begin[i] = c->pat_begin[i];
   a.npat = (int)c->pat_begin.size() - 1;
   {
-    double look = 8.0;  // in tiles per persistent CTA (measured on config 2: 0 -> 14.1 ms, 1.5 -> 13.8, 2.5 -> 13.4, 4 -> 12.9, 8 -> 12.9)
+    double look = 16.0;  // in tiles per persistent CTA (measured on config 2: 0 -> 14.1 ms, 1.5 -> 13.8, 2.5 -> 13.4, 4 -> 12.9, 8 -> 12.9;
+                         // a wave of 8 sources: 4 -> 27.6 ms, 8 -> 25.0, 16 -> 24.3, 32 -> 24.4)
     if (const char* e = getenv("SWEEPTT_LOOKAHEAD")) look = atof(e);
     a.lookahead = (unsigned)std::max(0.0, look * c->tl.grid_persistent);
     double frac = 0.4;  // (0.9 -> 14.8 ms, 0.6 -> 13.1, 0.4 -> 12.9, 0.1 -> 13.2)
@@ -2237,7 +2238,7 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
   return solve_slabs_impl(fetch, nx, ny, nz, fs, starsize, start, tt_out, opts, stats);
 }
 
-// Each slab reads only its own planes (+ ghost planes) straight from the .vbox file with the subset
+// Each part reads only the planes of its own blocks (+ halo planes) straight from the .vbox file with the subset
 // loader (include/velocityboxfiler.h:741 vbfileloadbinarysubset) -- the full model never has to fit
 // in host memory at once.
 extern "C" int sweeptt_solve_slabs_vbox(const char* vbox_path, const struct FS* fs, int starsize, struct START start,
