@@ -1265,6 +1265,9 @@ static int run_plan(sweeptt_ctx* c, sweeptt_stats* stats, const std::function<in
       cudaStream_t st = lane_stream(sl.lane);
       RelaxArgs a = slice_args(c, sl);
       TiledLaunch tl = c->tl;
+      // (early list builds: 8 tiles per CTA ahead for a few sources, 16 for a full wave -- measured: 4 sources 12.45
+      //  vs 12.70 ms, 8 sources 25.0 vs 24.3 ms)
+      if (sl.ns < 6 && !getenv("SWEEPTT_LOOKAHEAD")) a.lookahead /= 2;
       if (sl.grid > 0) {
         a.lookahead = (unsigned)((unsigned long long)a.lookahead * sl.grid / std::max(1, tl.grid_persistent));
         tl.grid_persistent = sl.grid;
