@@ -138,7 +138,12 @@ int sweeptt_debug_column_split(const struct FS *fs, int starsize, int nw, int *n
  * tt_out[s] (nx*ny*nz floats each) receives the converged field of source s; the library
  * initialises travel times itself (INF, 0 at the start; serial_new/...c:139-144).
  * With opts->num_devices > 1 the sources are sharded over the devices with no
- * inter-device communication (the mpi/backup.c:351-363 scheme). */
+ * inter-device communication (the mpi/backup.c:351-363 scheme).
+ * More sources than one single-launch solve holds run as consecutive waves; the fields of a finished
+ * wave are copied to tt_out[] while the next wave is relaxed.  tt_out[] may be page-locked
+ * (sweeptt_host_alloc) or plain malloc memory like the reference's boxalloc; the latter is served
+ * through a page-locked stop-over inside the library (the first box decides which way all boxes of a
+ * call go; either way is correct for any mix). */
 int sweeptt_solve(const float *slowness, int nx, int ny, int nz, const struct FS *fs, int starsize,
                   const struct START *starts, int numstart, float *const *tt_out,
                   const sweeptt_opts *opts, sweeptt_stats *stats);
