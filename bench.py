@@ -555,9 +555,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": tot["elapsed_ms"] / args.steps, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "sources_total": tot["sources"] // args.steps, "sources_on_rank0": nsrc,
-                   "loop": (f"{launches_per_step:.0f} single persistent launches per solve (waves of <= 8 sources, two at a time "
-                            "on half the SMs each; work lists built on the device; the roofline leg times them one at a "
-                            "time on the whole device)" if launches_per_step <= 64
+                   "loop": (f"{launches_per_step:.0f} single persistent launches per solve (waves of <= 8 sources back to back; "
+                            "work lists built on the device)" if launches_per_step <= 64
                             else "CUDA-graph WHILE of rounds (device-resident)"),
                    "l2": "flushed between timed steps (512 MiB write, untimed)",
                    "relax_definition": "one pull evaluation tt[n] <- min(tt[n], hd*(v_n+v_m)+tt[m]) with n,m in bounds"},

@@ -1090,7 +1090,10 @@ static int build_plan(sweeptt_ctx* c) {
   want_groups = std::max(1, std::min(want_groups, MAX_GROUPS));
   // Persistent waves may run K at a time, each on 1/K of the SMs (its own stream): a wave's start and end expose
   // fewer ready tiles than there are SMs (the front is small), and the time lost there shrinks with the SMs per wave.
-  int kstreams = 2;  // (measured on config 3, 111 sources: 1 stream 345.6 ms, 2 streams 338.2 ms, 4 streams 381.7 ms)
+  // (measured on config 3: 111 sources on 1 stream 345.6 / 348.7 ms, 2 streams 338.2 / 346.9 ms, 4 streams 381.7 ms --
+  //  but the SMs are split statically, so the stream that runs dry first idles its half: 28 sources in waves of
+  //  8+8+8+4 over 2 streams 94.0 ms against 87.2 ms on one.  One stream unless asked for.)
+  int kstreams = 1;
   if (const char* e = getenv("SWEEPTT_WAVE_STREAMS")) kstreams = std::max(1, std::min(atoi(e), MAX_GROUPS));
   const int nwaves_total = (c->nsrc + wave_size - 1) / wave_size;
   if (!persistent || nwaves_total < 2 * kstreams) kstreams = 1;
