@@ -1103,10 +1103,11 @@ static int build_plan(sweeptt_ctx* c) {
   // solve, so the last wave is kept small (4 sources) and the others share the rest evenly.
   std::vector<int> sizes;
   if (persistent && c->nsrc > wave_size && c->nsrc >= 8 && !getenv("SWEEPTT_WAVE")) {
-    const int rest = c->nsrc - 4;
+    const int last = std::min(4, wave_size);  // (a wave never exceeds what one launch holds)
+    const int rest = c->nsrc - last;
     const int nw = (rest + wave_size - 1) / wave_size;
     for (int w = 0; w < nw; ++w) sizes.push_back((int)((long long)rest * (w + 1) / nw - (long long)rest * w / nw));
-    sizes.push_back(4);
+    sizes.push_back(last);
   } else {
     for (int s0 = 0; s0 < c->nsrc; s0 += wave_size) sizes.push_back(std::min(wave_size, c->nsrc - s0));
   }
