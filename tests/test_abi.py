@@ -53,6 +53,12 @@ def test_compute_fails_loudly_without_a_gpu():
         P.solve(v, W.star("3"), [(0, 0, 0)])
     with pytest.raises(P.SweepError, match="no CUDA device"):
         P.SweepContext()
+    with pytest.raises(P.SweepError, match="no CUDA device"):
+        P.solve_slabs(v, W.star("3"), (0, 0, 0), num_slabs=2)
+    lib = P.load_library()
+    assert not lib.sweeptt_host_alloc(1 << 20), "page-locked memory cannot exist without a CUDA device"
+    assert b"no CUDA device" in lib.sweeptt_last_error()
+    lib.sweeptt_host_free(None)   # (a null pointer is accepted, like free())
 
 
 def test_star_distance_helper_matches_reference_formula():
