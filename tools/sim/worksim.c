@@ -12,6 +12,8 @@
 //
 // build: gcc -O3 -ffp-contract=off -o worksim worksim.c -lm
 // usage: worksim slowness.f32 nx ny nz star.txt sx sy sz [bucket_factor]
+// Three runs: all columns; column skipping by the useful-source window; per-unit dirty flags (all columns of the
+// dirty units).  Every run must end in the same field.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -31,7 +33,7 @@ static float *slow, *tt;
 static int *oi, *oj, *ok;
 static float *hd;
 static float *key, *tmaxv;
-static unsigned char *dirty;
+static unsigned char *udirty; static int use_units;
 static float dmin_, bucket;
 static unsigned *nstamp, *tvis, *tchg; static unsigned vclock;
 static unsigned long long ex_col_need, ex_col_all, ex_pull_need, ex_pull_all, nb_col_need;
@@ -55,6 +57,7 @@ static unsigned long long hist_frac[11];
 static unsigned long long fine_pull_useful, fine_pull_all, fine_off_useful, fine_off_all, improving_pulls;
 
 // returns 1 if anything changed; tmin_out = smallest lowered value
+static int g_chmask;
 static int visit(int tx, int ty, int tz, float K, int skip, float* tmin_out, int sxp, int syp, int szp) {
   static float sv[TX + 2 * R][TY + 2 * R][TZ + 2 * ZH], st[TX + 2 * R][TY + 2 * R][TZ + 2 * ZH];
   const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
@@ -95,8 +98,12 @@ static int visit(int tx, int ty, int tz, float K, int skip, float* tmin_out, int
   tvis[tself] = vclock;
   float tmin = INFINITY, tmx = 0.f;
   ++tile_visits;
+  g_chmask = 0;
+  const int tself2 = (tx * nty + ty) * ntz + tz;
   for (int u = 0; u < TX / 4; ++u) {
     if (x0 + 4 * u >= nx) continue;
+    if (use_units && !udirty[2 * tself2 + u]) continue;
+    udirty[2 * tself2 + u] = 0;
     ++unit_visits;
     // unit max over in-grid nodes
     float umax = 0.f;
@@ -167,7 +174,7 @@ static int visit(int tx, int ty, int tz, float K, int skip, float* tmin_out, int
       if (v < st[4 * u + a + R][b + R][c + ZH]) { uch = 1; tmin = fminf(tmin, v); tt[IDX(gx, gy, gz)] = v; nstamp[IDX(gx, gy, gz)] = vclock; tchg[tself] = vclock; }
       tmx = fmaxf(tmx, v);
     }
-    if (uch) { ++unit_changed; changed = 1; }
+    if (uch) { ++unit_changed; changed = 1; g_chmask |= 1 << u; }
   }
   tmaxv[(tx * nty + ty) * ntz + tz] = tmx;
   *tmin_out = tmin;
@@ -183,10 +190,10 @@ static void solve(int skip, int sxp, int syp, int szp) {
   const int ntiles = ntx * nty * ntz;
   for (size_t i = 0; i < (size_t)nx * ny * nz; ++i) tt[i] = INFINITY;
   tt[IDX(sxp, syp, szp)] = 0.f;
-  for (int i = 0; i < ntiles; ++i) { key[i] = INFINITY; tmaxv[i] = INFINITY; }
+  for (int i = 0; i < ntiles; ++i) { key[i] = INFINITY; tmaxv[i] = INFINITY; udirty[2 * i] = udirty[2 * i + 1] = 0; }
   for (int dx = -XR; dx <= XR; ++dx) for (int dy = -1; dy <= 1; ++dy) for (int dz = -1; dz <= 1; ++dz) {
     const int ux = sxp / TX + dx, uy = syp / TY + dy, uz = szp / TZ + dz;
-    if (ux >= 0 && ux < ntx && uy >= 0 && uy < nty && uz >= 0 && uz < ntz) key[(ux * nty + uy) * ntz + uz] = 0.f;
+    if (ux >= 0 && ux < ntx && uy >= 0 && uy < nty && uz >= 0 && uz < ntz) { key[(ux * nty + uy) * ntz + uz] = 0.f; udirty[2 * ((ux * nty + uy) * ntz + uz)] = udirty[2 * ((ux * nty + uy) * ntz + uz) + 1] = 1; }
   }
   memset(nstamp, 0, 4 * (size_t)nx * ny * nz); memset(tvis, 0, 4 * ntiles); memset(tchg, 0, 4 * ntiles); vclock = 1;
   nstamp[IDX(sxp, syp, szp)] = 1;
@@ -221,6 +228,10 @@ static void solve(int skip, int sxp, int syp, int szp) {
         const int self = !dx && !dy && !dz;
         if (!self && !((tmin + dmin_) < tmaxv[u])) continue;
         if (tmin < key[u]) key[u] = tmin;
+        for (int cu = 0; cu < 2; ++cu) if (g_chmask & (1 << cu)) for (int vu = 0; vu < 2; ++vu) {
+          const int U = 2 * tx + cu, V = 2 * ux + vu;
+          if (abs(U - V) <= 2) udirty[2 * u + vu] = 1;
+        }
       }
     }
   }
@@ -274,12 +285,22 @@ int main(int argc, char** argv) {
   dmin_ = hdmin * (vmin + vmin);
   ntx = (nx + TX - 1) / TX; nty = (ny + TY - 1) / TY; ntz = (nz + TZ - 1) / TZ;
   key = malloc(4 * ntx * nty * ntz); tmaxv = malloc(4 * ntx * nty * ntz);
+  udirty = malloc(2 * ntx * nty * ntz);
   nstamp = malloc(4 * vol); tvis = malloc(4 * ntx * nty * ntz); tchg = malloc(4 * ntx * nty * ntz);
   printf("%d x %d x %d, %d offsets in %d columns, bucket %.2f, dmin %.3f\n", nx, ny, nz, nstar, ncols, bucket, dmin_);
+  use_units = 0;
   solve(0, sxp, syp, szp);
   float* ref = malloc(vol * 4);
   memcpy(ref, tt, vol * 4);
   solve(1, sxp, syp, szp);
+  size_t nd0 = 0;
+  for (size_t i = 0; i < vol; ++i) nd0 += memcmp(&ref[i], &tt[i], 4) != 0;
+  // third policy: tile-level keys as before, plus a dirty flag per 4x8x8 UNIT (set by a changed unit within reach,
+  // |unit index difference| <= 2); a visit relaxes only the dirty units
+  use_units = 1;
+  printf("per-unit dirty flags:\n");
+  solve(0, sxp, syp, szp);
+  if (nd0) { printf("column skipping changed %zu floats\n", nd0); return 1; }
   size_t nd = 0;
   for (size_t i = 0; i < vol; ++i) nd += memcmp(&ref[i], &tt[i], 4) != 0;
   printf("fields differ in %zu of %zu floats\n", nd, vol);
