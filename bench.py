@@ -604,7 +604,7 @@ def run_ours(args):
             "kernel_ms_per_sweep": {k: v.get("kernel_ms_per_sweep_mean") for k, v in lg["variants"].items()},
             "sweeps_per_source": {k: v.get("sweeps_per_source") for k, v in lg["variants"].items()},
             "output_tt_equals_ours": {k: v.get("output_tt_equals_ours") for k, v in lg["variants"].items()},
-            "ours_ms_per_converged_source": tot["elapsed_ms"] / max(1, tot["sources"]),
+            "ours_ms_per_converged_source_per_gpu": tot["elapsed_ms"] * world / max(1, tot["sources"]),
         }
     except Exception:
         pass
