@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -335,17 +337,33 @@ extern "C" int sweeptt_starts_load(const char* path, struct START** starts, int*
 // ---------------------------------------------------------------------------------------
 namespace {
 
+// "00".."99"
+struct Digits2 {
+  char t[200];
+  Digits2() { for (int i = 0; i < 100; ++i) { t[2 * i] = (char)('0' + i / 10); t[2 * i + 1] = (char)('0' + i % 10); } }
+};
+const Digits2 kDigits2;
+
 inline char* put_uint(char* p, unsigned v) {
   char tmp[12];
   int n = 0;
-  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (v >= 100) { const unsigned r = v % 100; v /= 100; tmp[n++] = kDigits2.t[2 * r + 1]; tmp[n++] = kDigits2.t[2 * r]; }
+  if (v >= 10) { tmp[n++] = kDigits2.t[2 * v + 1]; tmp[n++] = kDigits2.t[2 * v]; } else tmp[n++] = (char)('0' + v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char* put_u64(char* p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  while (v >= 100) { const unsigned r = (unsigned)(v % 100); v /= 100; tmp[n++] = kDigits2.t[2 * r + 1]; tmp[n++] = kDigits2.t[2 * r]; }
+  if (v >= 10) { tmp[n++] = kDigits2.t[2 * v + 1]; tmp[n++] = kDigits2.t[2 * v]; } else tmp[n++] = (char)('0' + v);
   while (n) *p++ = tmp[--n];
   return p;
 }
 
-// printf("%f") of a float, byte-identical to glibc for finite values below 2^39: the binary
-// value m*2^e is scaled by 10^6 in exact integer arithmetic and rounded half-to-even, which is
-// what glibc does in the default rounding mode.  Everything else goes through snprintf.
+// printf("%f") of a float, byte-identical to glibc for finite values below 2^39: the binary value m*2^e is scaled by
+// 10^6 in exact integer arithmetic (m * 10^6 < 2^44, shifted left by at most 15 or right with the remainder kept) and
+// rounded half-to-even, which is what glibc does in the default rounding mode.  Everything else goes through snprintf.
 inline char* put_float_f(char* p, float x) {
   uint32_t bits;
   std::memcpy(&bits, &x, 4);
@@ -355,51 +373,55 @@ inline char* put_float_f(char* p, float x) {
   uint64_t m = bits & 0x7fffffu;
   int e;
   if (expo == 0) e = -149; else { m |= 0x800000u; e = (int)expo - 150; }
-  unsigned __int128 scaled = (unsigned __int128)m * 1000000u;  // < 2^44
+  const uint64_t scaled = m * 1000000u;  // < 2^44
   uint64_t q;
   if (e >= 0) {
-    q = (uint64_t)(scaled << e);  // < 2^44 * 2^15 * ... bounded by the 2^39 guard above
-  } else if (-e >= 100) {
-    q = 0;
+    q = scaled << e;  // e <= 15 by the guard above: < 2^59
+  } else if (-e >= 46) {
+    q = 0;            // scaled < 2^44 <= half a unit of the last decimal
   } else {
     const int sh = -e;
-    const unsigned __int128 one = (unsigned __int128)1 << sh;
-    const unsigned __int128 rem = scaled & (one - 1);
-    q = (uint64_t)(scaled >> sh);
-    const unsigned __int128 half = one >> 1;
+    const uint64_t one = (uint64_t)1 << sh;
+    const uint64_t rem = scaled & (one - 1);
+    q = scaled >> sh;
+    const uint64_t half = one >> 1;
     if (rem > half || (rem == half && (q & 1))) ++q;
   }
   const uint64_t ip = q / 1000000u;
-  unsigned fp = (unsigned)(q % 1000000u);
-  char tmp[24];
-  int n = 0;
-  uint64_t t = ip;
-  do { tmp[n++] = (char)('0' + t % 10); t /= 10; } while (t);
-  while (n) *p++ = tmp[--n];
+  const unsigned fp = (unsigned)(q - ip * 1000000u);
+  p = ip < 0x100000000ull ? put_uint(p, (unsigned)ip) : put_u64(p, ip);
   *p++ = '.';
-  for (int d = 5; d >= 0; --d) { p[d] = (char)('0' + fp % 10); fp /= 10; }
+  const unsigned a = fp / 10000u, bc = fp - a * 10000u, b = bc / 100u, c = bc - b * 100u;
+  std::memcpy(p, &kDigits2.t[2 * a], 2);
+  std::memcpy(p + 2, &kDigits2.t[2 * b], 2);
+  std::memcpy(p + 4, &kDigits2.t[2 * c], 2);
   return p + 6;
 }
 
-// formats rows [i0,i1) of one source's box
-void format_slab(const float* tt, int i0, int i1, int ny, int nz, std::string& out) {
-  out.clear();
-  out.reserve((size_t)(i1 - i0) * ny * nz * 48);
-  char line[160];
+// worst-case bytes of one line: prefix 17 + three ints (<= 10 digits) + 2 commas + "): " + %f (<= 48) + " 0 0 0\n"
+constexpr size_t kLineMax = 17 + 30 + 2 + 3 + 48 + 7;
+
+// formats rows [i0,i1) of one source's box into buf (capacity: rows * ny * nz * kLineMax); returns the bytes written
+size_t format_slab(const float* tt, int i0, int i1, int ny, int nz, char* buf) {
+  char* p = buf;
   const float* v = tt + (size_t)i0 * ny * nz;
+  char prefix[64];
   for (int i = i0; i < i1; ++i)
-    for (int j = 0; j < ny; ++j)
+    for (int j = 0; j < ny; ++j) {
+      char* q = prefix;
+      std::memcpy(q, "travel time for (", 17); q += 17;
+      q = put_uint(q, (unsigned)i); *q++ = ',';
+      q = put_uint(q, (unsigned)j); *q++ = ',';
+      const size_t plen = (size_t)(q - prefix);
       for (int k = 0; k < nz; ++k) {
-        char* p = line;
-        std::memcpy(p, "travel time for (", 17); p += 17;
-        p = put_uint(p, (unsigned)i); *p++ = ',';
-        p = put_uint(p, (unsigned)j); *p++ = ',';
+        std::memcpy(p, prefix, plen); p += plen;
         p = put_uint(p, (unsigned)k);
         std::memcpy(p, "): ", 3); p += 3;
         p = put_float_f(p, *v++);
         std::memcpy(p, " 0 0 0\n", 7); p += 7;
-        out.append(line, (size_t)(p - line));
       }
+    }
+  return (size_t)(p - buf);
 }
 
 }  // namespace
@@ -411,23 +433,46 @@ extern "C" int sweeptt_write_output_tt(const char* path, const float* const* tt,
   std::fprintf(f, "%d %d %d\n", nx, ny, nz);
   unsigned nthreads = std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
-  nthreads = std::min<unsigned>(nthreads, 16);
+  nthreads = std::min<unsigned>(nthreads, 32);
   if (const char* env = std::getenv("SWEEPTT_IO_THREADS")) nthreads = std::max(1, std::atoi(env));
   nthreads = std::min<unsigned>(nthreads, (unsigned)nx);
+  // The text of one source is formatted in x-slabs by worker threads while the text of the source before it is being
+  // written: two sets of slab buffers (sized for the worst case; only the pages actually written become resident).
+  struct Slab { std::unique_ptr<char[]> buf; size_t cap = 0, len = 0; };
+  std::vector<Slab> sets[2];
+  for (auto& set : sets) set.resize(nthreads);
+  auto slab_rows = [&](unsigned t, int* i0, int* i1) {
+    *i0 = (int)((long long)nx * t / nthreads); *i1 = (int)((long long)nx * (t + 1) / nthreads);
+  };
+  for (unsigned t = 0; t < nthreads; ++t) {
+    int i0, i1;
+    slab_rows(t, &i0, &i1);
+    const size_t cap = (size_t)(i1 - i0) * ny * nz * kLineMax + 64;
+    for (auto& set : sets) { set[t].buf.reset(new (std::nothrow) char[cap]); set[t].cap = cap; }
+    if (!sets[0][t].buf || !sets[1][t].buf) { std::fclose(f); return sweeptt::set_error("out of memory for the output.tt buffers"); }
+  }
+  auto launch = [&](int s, std::vector<std::thread>& th) {
+    th.clear();
+    for (unsigned t = 0; t < nthreads; ++t) {
+      int i0, i1;
+      slab_rows(t, &i0, &i1);
+      Slab* sl = &sets[s & 1][t];
+      const float* src = tt[s];
+      th.emplace_back([=] { sl->len = format_slab(src, i0, i1, ny, nz, sl->buf.get()); });
+    }
+  };
   bool ok = true;
-  std::vector<std::string> chunks(nthreads);
-  for (int s = 0; s < numstart && ok; ++s) {
-    std::fprintf(f, "starting point: %d\n", s);
-    // the text of one source is formatted in x-slabs by worker threads, written in order
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nthreads; ++t) {
-      const int i0 = (int)((long long)nx * t / nthreads), i1 = (int)((long long)nx * (t + 1) / nthreads);
-      th.emplace_back(format_slab, tt[s], i0, i1, ny, nz, std::ref(chunks[t]));
+  std::vector<std::thread> cur, next;
+  if (numstart > 0) launch(0, cur);
+  for (int s = 0; s < numstart; ++s) {
+    for (auto& t : cur) t.join();
+    if (s + 1 < numstart) launch(s + 1, next);  // formats into the other set while this one is written
+    if (ok) {
+      std::fprintf(f, "starting point: %d\n", s);
+      for (unsigned t = 0; t < nthreads && ok; ++t)
+        ok = std::fwrite(sets[s & 1][t].buf.get(), 1, sets[s & 1][t].len, f) == sets[s & 1][t].len;
     }
-    for (unsigned t = 0; t < nthreads; ++t) {
-      th[t].join();
-      ok = ok && std::fwrite(chunks[t].data(), 1, chunks[t].size(), f) == chunks[t].size();
-    }
+    cur.swap(next);
   }
   ok = (std::fclose(f) == 0) && ok;
   return ok ? 1 : sweeptt::set_error("error writing %s", path);
