@@ -191,13 +191,19 @@ extern "C" int sweeptt_vbox_load_subset(const char* path, const int so[3], const
     std::fclose(f);
     return sweeptt::set_error("unable to allocate memory for the subset");
   }
-  // one seek + one read per z strip (include/velocityboxfiler.h:804-826); checksum not verified
+  // One seek + one read per contiguous run; checksum not verified (include/velocityboxfiler.h:798-826 reads z strip
+  // by z strip).  Strips that span the stored z range are contiguous over y, planes that also span the stored y range
+  // are contiguous over x: a slab of whole planes -- what one part of a multi-device grid loads -- is ONE read.
   bool ok = true;
-  for (int x = 0; x < sd[0] && ok; ++x)
-    for (int y = 0; y < sd[1] && ok; ++y) {
+  const bool full_z = so[2] == 0 && sd[2] == h.dims[2];
+  const bool full_y = full_z && so[1] == 0 && sd[1] == h.dims[1];
+  const size_t run = full_y ? vol : full_z ? (size_t)sd[1] * sd[2] : (size_t)sd[2];   // floats per read
+  const int nx_runs = full_y ? 1 : sd[0], ny_runs = full_z ? 1 : sd[1];
+  for (int x = 0; x < nx_runs && ok; ++x)
+    for (int y = 0; y < ny_runs && ok; ++y) {
       const long long pos = h.datapos + 4LL * (((long long)(x + so[0]) * h.dims[1] + (y + so[1])) * h.dims[2] + so[2]);
       ok = fseeko(f, (off_t)pos, SEEK_SET) == 0 &&
-           std::fread(v + ((size_t)x * sd[1] + y) * sd[2], 4, sd[2], f) == (size_t)sd[2];
+           std::fread(v + ((size_t)x * sd[1] + y) * sd[2], 4, run, f) == run;
     }
   std::fclose(f);
   if (!ok) {
