@@ -2236,6 +2236,10 @@ extern "C" int sweeptt_solve_slabs(const float* slowness, int nx, int ny, int nz
                                    struct START start, float* tt_out, const sweeptt_opts* opts, sweeptt_stats* stats) {
   if (!slowness) return fail("sweeptt_solve_slabs: null argument");
   auto fetch = [&](const int* org, const int* dims, float* dst) -> int {
+    if (org[1] == 0 && org[2] == 0 && dims[1] == ny && dims[2] == nz) {  // whole planes: one contiguous run
+      std::memcpy(dst, slowness + (size_t)org[0] * ny * nz, sizeof(float) * (size_t)dims[0] * ny * nz);
+      return 1;
+    }
     for (int x = 0; x < dims[0]; ++x)
       for (int y = 0; y < dims[1]; ++y)
         std::memcpy(dst + ((size_t)x * dims[1] + y) * dims[2],
