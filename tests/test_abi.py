@@ -67,3 +67,42 @@ def test_star_distance_helper_matches_reference_formula():
         i, j, k = fs[l].i, fs[l].j, fs[l].k
         want = np.float32(10.0) * np.float32(np.sqrt(np.float64(i * i + j * j + k * k)))
         assert np.float32(fs[l].d) == want
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/sweeptt.h compiles as strict C99 and a C client links against libsweeptt.so (the binding a reference
+    maintainer would add); run without a GPU it must fail loudly, not crash."""
+    import subprocess
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "sweeptt.h"
+int main(void) {
+  struct FS fs[3] = {{1, 0, 0, 0.f}, {0, 1, 0, 0.f}, {0, 0, 1, 0.f}};
+  struct START st[1] = {{0, 0, 0}};
+  float v[8] = {1, 1, 1, 1, 1, 1, 1, 1}, t[8];
+  float *out[1];
+  sweeptt_opts opts;
+  sweeptt_stats stats;
+  int i;
+  for (i = 0; i < (int)sizeof opts; i++) ((char *)&opts)[i] = 0;
+  opts.struct_size = (int)sizeof opts;
+  opts.device = -1;
+  out[0] = t;
+  sweeptt_star_fill_distances(fs, 3, 10.0f);
+  if (fs[0].d != 10.0f) return 3;
+  if (sweeptt_device_count() > 0) return 0;  /* (GPU box: covered by the gpu tests) */
+  if (sweeptt_solve(v, 2, 2, 2, fs, 3, st, 1, out, &opts, &stats)) return 4;  /* must FAIL without a device */
+  printf("%s\n", sweeptt_last_error());
+  return 0;
+}
+''')
+    exe = tmp_path / "client"
+    lib = P.lib_path()
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-o", str(exe), str(src),
+                    f"-L{lib.parent}", "-lsweeptt", f"-Wl,-rpath,{lib.parent}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    if not torch.cuda.is_available():
+        assert "no CUDA device" in r.stdout
