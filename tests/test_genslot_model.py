@@ -17,6 +17,6 @@ def _run(exe, protocol, runs):
 def test_slot_recycling_protocol(tmp_path):
     exe = tmp_path / "genslot_model"
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), str(ROOT / "tests" / "native" / "genslot_model.cpp")], check=True)
-    assert _run(exe, "word", 3000) == (0, 0)
-    double, lost = _run(exe, "split", 3000)
+    assert _run(exe, "word", 1500) == (0, 0)
+    double, lost = _run(exe, "split", 1500)
     assert double > 0 and lost == 0, "the model should reproduce round 1's double hand-out"
