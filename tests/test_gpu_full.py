@@ -119,3 +119,24 @@ def test_scaled_config4_like_box_matches_reference_hashes():
         _check(tt[s], g, g["label"])
     one, _ = P.solve_slabs(v, W.star("818"), gold[0]["start"], num_slabs=3, slab_axis=0)
     _check(one, gold[0], gold[0]["label"] + " as one grid over 3 parts")
+
+
+def test_every_recorded_row_of_config3_matches_the_reference_hash():
+    """tests/golden/config3_all.json (tools/make_golden.py config3_all): sha256 of the converged field of every further
+    row of docs/start-111 that the reference's own code was run on in the build container.  All of them are solved
+    in one go -- waves of single-launch solves, exactly what bench.py times -- and compared."""
+    path = ROOT / "tests" / "golden" / "config3_all.json"
+    if not path.exists():
+        pytest.skip("tests/golden/config3_all.json not generated")
+    gold = json.loads(path.read_text())
+    if not gold:
+        pytest.skip("no rows recorded")
+    v = W.heterogeneous_field((241, 241, 51), seed=7)
+    assert hashlib.sha256(v.tobytes()).hexdigest() == gold[0]["v_sha256"]
+    s111 = W.starts(111)
+    rows = [int(g["label"].rsplit("row", 1)[1]) for g in gold]
+    for r, g in zip(rows, gold):
+        assert list(map(int, s111[r])) == g["start"]
+    tt, st = P.solve(v, W.star("818"), s111[rows], kernel=api.KERNEL_TILED)
+    bad = [g["label"] for s, g in enumerate(gold) if hashlib.sha256(tt[s].tobytes()).hexdigest() != g["tt_sha256"]]
+    assert not bad, f"{len(bad)} of {len(gold)} fields differ from the reference: {bad[:5]}"

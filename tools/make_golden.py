@@ -4,6 +4,7 @@ serial_new/sweep-tt-multistart.c compiled in the build container).
 
   python tools/make_golden.py small     -> tests/golden/small_cases.npz   (seconds)
   python tools/make_golden.py full      -> tests/golden/full_241.json     (~15-25 min, 5 processes)
+  python tools/make_golden.py config3_all [P] -> tests/golden/config3_all.json (every other row of start-111, sha256 only)
   python tools/make_golden.py more [P]  -> tests/golden/full_241_more.json (round 2: 9 further config-3 sources,
                                            full-size 5-FS and a scaled config-4-like box; P processes, ~1 h on 6)
 
@@ -116,5 +117,29 @@ def more():
             print(r["label"], r["ref_sweeps"], r["seconds"], r["tt_sha256"][:16], flush=True)
 
 
+def _sha_only(job):
+    r = _full_one(job)
+    r.pop("sample_bits", None); r.pop("sample_stride", None)
+    return r
+
+
+def config3_all():
+    """Every row of docs/start-111 that full_241_more.json does not hold yet: sha256 + sweep count only (0.3 KB each),
+    into tests/golden/config3_all.json -- ~15 min per source per core."""
+    procs = int(sys.argv[2]) if len(sys.argv) > 2 else 7
+    s111 = W.starts(111)
+    out = GOLD / "config3_all.json"
+    res = json.loads(out.read_text()) if out.exists() else []
+    have = {r["label"] for r in res}
+    jobs = [(f"config3_hetero_818_row{i}", "hetero", 7, "818", tuple(int(c) for c in s111[i]))
+            for i in range(111) if i not in MORE_C3 and f"config3_hetero_818_row{i}" not in have]
+    with mp.Pool(procs) as pool:
+        for r in pool.imap_unordered(_sha_only, jobs):
+            res.append(r)
+            res.sort(key=lambda x: int(x["label"].rsplit("row", 1)[1]))
+            out.write_text(json.dumps(res, indent=0))
+            print(r["label"], r["ref_sweeps"], r["seconds"], r["tt_sha256"][:16], flush=True)
+
+
 if __name__ == "__main__":
-    {"small": small, "full": full, "more": more}[sys.argv[1]]()
+    {"small": small, "full": full, "more": more, "config3_all": config3_all}[sys.argv[1]]()
