@@ -35,7 +35,11 @@ extern "C" {
 #endif
 
 /* serial_new/sweep-tt-multistart.c:46-49 (and cuda/cudasweep-tt-multistart.cu:58-61):
- * forward-star offset and its distance d = delta * sqrt(i*i+j*j+k*k). Layout kept. */
+ * forward-star offset and its distance d = delta * sqrt(i*i+j*j+k*k). Layout kept.
+ * A translation unit that already defines these two structs itself -- the reference's own
+ * programs do -- defines SWEEPTT_NO_STRUCTS before including this header (after its own
+ * definitions) and passes its arrays as they are. */
+#ifndef SWEEPTT_NO_STRUCTS
 struct FS {
   int i, j, k;
   float d;
@@ -45,6 +49,7 @@ struct FS {
 struct START {
   int i, j, k;
 };
+#endif
 
 /* which relaxation kernel runs (the default is the tiled sm_100a kernel) */
 enum {
